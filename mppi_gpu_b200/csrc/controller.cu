@@ -1,0 +1,673 @@
+// controller.cu -- host side of the B200 MPPI core and its C ABI (include/mppi_b200.h).
+//
+// Counterpart of the reference's host object PointMassModel (include/point_mass.hpp:23-116,
+// src/point_mass.cu:19-491): owns every device buffer of one K-shard, builds the control
+// step as a CUDA graph once and replays it per step.  Where the reference issues ~3T+8
+// launches and as many cudaDeviceSynchronize() per get_act (src/point_mass.cu:129-203,
+// :384-480), one step here is one cudaGraphLaunch of 5 kernels + a 4A-byte D2H copy node.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mppi_b200.h"
+#include "comm.hpp"
+#include "kernels.cuh"
+
+using namespace mppi;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return fail(MPPI_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,       \
+                        cudaGetErrorString(e__));                                         \
+    } while (0)
+
+constexpr int kStageSlots = 16;   // pinned staging ring for set_state
+
+}  // namespace
+
+struct mppi_handle {
+    mppi_params p{};
+    cudaStream_t stream = nullptr;
+    LaunchCtx ctx{};
+    int R = 0, S = 0;
+
+    float *d_eps = nullptr, *d_S = nullptr, *d_wt = nullptr, *d_partials = nullptr;
+    float *d_eta_part = nullptr, *d_red = nullptr, *d_U = nullptr, *d_Uprev = nullptr;
+    float *d_next = nullptr;
+    ProblemDev *d_prob = nullptr;
+    CtlDev *d_ctl = nullptr;
+
+    ProblemDev h_prob{};
+    float *h_stage = nullptr;     // pinned [kStageSlots][2*kMaxAct]
+    int stage_slot = 0;
+    float *h_next = nullptr;      // pinned [kMaxAct]
+
+    CUtensorMap tmap{};
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // [0] sampling, [1] injected noise
+    NcclComm comm;
+
+    bool problem_set = false;
+    bool injected = false;
+    bool profiling = false;
+    bool pending = false;
+
+    cudaEvent_t ev[MPPI_K_COUNT + 1] = {};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    double ms_sum[MPPI_K_COUNT] = {};
+    int64_t launches[MPPI_K_COUNT] = {};
+    int64_t total_launches = 0;
+};
+
+namespace {
+
+bool multi(const mppi_handle *h) { return h->p.world_size > 1; }
+bool fused(const mppi_handle *h) { return (h->p.flags & MPPI_FLAG_FUSED_SAMPLING) != 0; }
+
+int encode_tmap(mppi_handle *h)
+{
+    typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+        return fail(MPPI_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    const cuuint64_t gdim[2] = {(cuuint64_t)h->ctx.k_pad, (cuuint64_t)h->R};
+    const cuuint64_t gstride[1] = {(cuuint64_t)h->ctx.k_pad * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kAvgTileK, (cuuint32_t)kAvgTileR};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiled>(fn)(
+        &h->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->d_eps, gdim, gstride, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MPPI_ERR_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+    return MPPI_OK;
+}
+
+// Enqueue the kernel chain of one control step on h->stream.  evs (optional) receives one
+// event before the first kernel and one after each stage (profiling mode).
+int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
+{
+    const LaunchCtx &c = h->ctx;
+    std::string err;
+    int ei = 0;
+    auto mark = [&](void) -> cudaError_t {
+        return evs ? cudaEventRecord(evs[ei++], c.stream) : cudaSuccess;
+    };
+    CK(mark());
+    if (sample && !fused(h)) CK(launch_sample(c, h->d_eps, h->d_prob, h->d_ctl, false, 0));
+    CK(mark());
+    CK(launch_rollout(c, h->d_eps, h->d_U, h->d_prob, h->d_S, h->d_ctl, sample && fused(h)));
+    CK(mark());
+    if (multi(h)) {
+        if (!h->comm.allreduce_min_u64(&h->d_ctl->min_key, 1, c.stream, err))
+            return fail(MPPI_ERR_COMM, "%s", err.c_str());
+    }
+    CK(mark());
+    CK(launch_weights(c, h->d_S, h->d_prob, h->d_ctl, h->d_wt, h->d_eta_part));
+    CK(mark());
+    CK(launch_average(c, h->tmap, h->d_wt, h->d_partials));
+    CK(mark());
+    if (multi(h)) {
+        CK(launch_finalize(c, true, false, h->d_partials, h->d_eta_part, h->d_red, h->d_U,
+                           h->d_Uprev, h->d_prob, h->d_ctl, h->d_next, h->p.flags));
+        if (!h->comm.allreduce_sum_f32(h->d_red, (size_t)h->R + 1, c.stream, err))
+            return fail(MPPI_ERR_COMM, "%s", err.c_str());
+        CK(mark());
+        CK(launch_finalize(c, false, true, h->d_partials, h->d_eta_part, h->d_red, h->d_U,
+                           h->d_Uprev, h->d_prob, h->d_ctl, h->d_next, h->p.flags));
+    } else {
+        CK(mark());
+        CK(launch_finalize(c, true, true, h->d_partials, h->d_eta_part, h->d_red, h->d_U,
+                           h->d_Uprev, h->d_prob, h->d_ctl, h->d_next, h->p.flags));
+    }
+    CK(cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * h->p.act_dim, cudaMemcpyDeviceToHost,
+                       c.stream));
+    CK(mark());
+    return MPPI_OK;
+}
+
+int kernels_per_step(const mppi_handle *h, bool sample)
+{
+    int n = 4;                                  // rollout, weights, average, finalize
+    if (sample && !fused(h)) n += 1;            // sampling
+    if (multi(h)) n += 1;                       // finalize split in fold + update
+    return n;
+}
+
+int build_graph(mppi_handle *h, int which)
+{
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_chain(h, which == 0, nullptr);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    if (rc != MPPI_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "cudaStreamEndCapture -> %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->graph_exec[which], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+    return MPPI_OK;
+}
+
+int upload_problem(mppi_handle *h)
+{
+    CK(cudaMemcpyAsync(h->d_prob, &h->h_prob, sizeof(ProblemDev), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int check_handle(mppi_handle *h)
+{
+    if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->p.device));
+    return MPPI_OK;
+}
+
+}  // namespace
+
+// ===================================================================================
+// C ABI
+// ===================================================================================
+extern "C" {
+
+int mppi_abi_version(void) { return MPPI_ABI_VERSION; }
+
+const char *mppi_last_error(void) { return g_last_error.c_str(); }
+
+const char *mppi_kernel_name(int id)
+{
+    static const char *names[MPPI_K_COUNT] = {"sample", "rollout", "comm_min", "weights",
+                                              "average", "comm_sum", "finalize"};
+    return (id >= 0 && id < MPPI_K_COUNT) ? names[id] : "?";
+}
+
+int mppi_params_default(mppi_params *p)
+{
+    if (!p) return fail(MPPI_ERR_INVALID, "null params");
+    memset(p, 0, sizeof *p);
+    p->struct_size = sizeof *p;
+    p->lambda = 1.0f;                               /* src/point_mass.cu:53-54 */
+    for (int a = 0; a < MPPI_MAX_ACT; ++a) {
+        p->sigma[a] = 0.025f;                       /* src/point_mass_gpu.cu:86 */
+        p->inv_sigma[a] = 1.0f;                     /* src/point_mass_gpu.cu:58-61 */
+        p->init_act[a] = 0.0f;
+        p->max_act[a] = 1.0f;
+    }
+    p->world_size = 1;
+    p->comm = MPPI_COMM_NONE;
+    return MPPI_OK;
+}
+
+int mppi_comm_unique_id(uint8_t id[MPPI_COMM_ID_BYTES])
+{
+    std::string err;
+    if (!NcclComm::unique_id(id, err)) return fail(MPPI_ERR_COMM, "%s", err.c_str());
+    return MPPI_OK;
+}
+
+int mppi_destroy(mppi_handle *h)
+{
+    if (!h) return MPPI_OK;
+    cudaSetDevice(h->p.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto &g : h->graph_exec) if (g) cudaGraphExecDestroy(g);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->t0) cudaEventDestroy(h->t0);
+    if (h->t1) cudaEventDestroy(h->t1);
+    cudaFree(h->d_eps); cudaFree(h->d_S); cudaFree(h->d_wt); cudaFree(h->d_partials);
+    cudaFree(h->d_eta_part); cudaFree(h->d_red); cudaFree(h->d_U); cudaFree(h->d_Uprev);
+    cudaFree(h->d_next); cudaFree(h->d_prob); cudaFree(h->d_ctl);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->h_next) cudaFreeHost(h->h_next);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MPPI_OK;
+}
+
+int mppi_create(const mppi_params *params, mppi_handle **out)
+{
+    if (!params || !out) return fail(MPPI_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (params->struct_size != sizeof(mppi_params))
+        return fail(MPPI_ERR_INVALID, "mppi_params.struct_size %u != %zu (ABI mismatch)",
+                    params->struct_size, sizeof(mppi_params));
+    const mppi_params &p = *params;
+    if (p.act_dim < 1 || p.act_dim > MPPI_MAX_ACT)
+        return fail(MPPI_ERR_INVALID, "act_dim %d not in [1,%d]", p.act_dim, MPPI_MAX_ACT);
+    if (p.state_dim != 2 * p.act_dim)
+        return fail(MPPI_ERR_INVALID, "state_dim %d must be 2*act_dim (point mass: positions, velocities)",
+                    p.state_dim);
+    if (p.samples < 1 || p.samples > 0xffffffffll)
+        return fail(MPPI_ERR_INVALID, "samples %lld out of range", (long long)p.samples);
+    if (p.horizon < 1 || (long long)p.horizon * p.act_dim > (1 << 20))
+        return fail(MPPI_ERR_INVALID, "horizon %d out of range", p.horizon);
+    if (!(p.lambda > 0.0f)) return fail(MPPI_ERR_INVALID, "lambda must be > 0");
+    if (p.world_size < 1 || p.rank < 0 || p.rank >= p.world_size)
+        return fail(MPPI_ERR_INVALID, "rank %d / world_size %d invalid", p.rank, p.world_size);
+    if (p.world_size > 1 && p.comm != MPPI_COMM_NCCL)
+        return fail(MPPI_ERR_INVALID, "world_size > 1 needs comm = MPPI_COMM_NCCL");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MPPI_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+    }
+    if (p.device < 0 || p.device >= ndev)
+        return fail(MPPI_ERR_INVALID, "device %d out of range (%d devices)", p.device, ndev);
+    CK(cudaSetDevice(p.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, p.device));
+    if (prop.major != 10)
+        return fail(MPPI_ERR_NO_DEVICE, "device %d is sm_%d%d; this build is sm_100a only",
+                    p.device, prop.major, prop.minor);
+
+    mppi_handle *h = new mppi_handle();
+    h->p = p;
+    h->R = p.horizon * p.act_dim;
+    h->S = p.state_dim;
+    h->injected = (p.flags & MPPI_FLAG_INJECTED_NOISE) != 0;
+
+    // K-shard geometry: whole Philox quads (4 samples) per shard so that eps[k] depends on
+    // the global k only, whatever the number of shards.
+    int64_t k0 = 0, k1 = 0;
+    mppi_shard_range(p.samples, p.rank, p.world_size, &k0, &k1);
+    if (k1 <= k0) { delete h; return fail(MPPI_ERR_INVALID, "shard %d of %d is empty", p.rank, p.world_size); }
+
+    LaunchCtx &c = h->ctx;
+    c.act_dim = p.act_dim;
+    c.horizon = p.horizon;
+    c.rows = h->R;
+    c.k_local = k1 - k0;
+    c.k_offset = k0;
+    c.k_pad = (c.k_local + kKPad - 1) / kKPad * kKPad;
+    c.seed = p.seed;
+    c.strict = (p.flags & MPPI_FLAG_STRICT_ARITH) != 0;
+    c.num_sms = prop.multiProcessorCount;
+    const long long ntiles = (c.k_pad / kAvgTileK) * (long long)((h->R + kAvgTileR - 1) / kAvgTileR);
+    c.avg_grid = (int)(ntiles < c.num_sms ? ntiles : c.num_sms);
+    c.avg_gpad = (c.avg_grid + 31) / 32 * 32;
+    c.weights_blocks = (int)((c.k_pad + kWeightsBlockSamples - 1) / kWeightsBlockSamples);
+
+    int rc = MPPI_OK;
+#define CKH(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            rc = fail(MPPI_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,         \
+                      cudaGetErrorString(e__));                                           \
+            mppi_destroy(h);                                                              \
+            return rc;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+    CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    c.stream = h->stream;
+    const size_t eps_bytes = sizeof(float) * (size_t)h->R * (size_t)c.k_pad;
+    CKH(cudaMalloc(&h->d_eps, eps_bytes));
+    CKH(cudaMalloc(&h->d_S, sizeof(float) * (size_t)c.k_pad));
+    CKH(cudaMalloc(&h->d_wt, sizeof(float) * (size_t)c.k_pad));
+    CKH(cudaMalloc(&h->d_partials, sizeof(float) * (size_t)h->R * c.avg_gpad));
+    CKH(cudaMalloc(&h->d_eta_part, sizeof(float) * (size_t)c.weights_blocks));
+    CKH(cudaMalloc(&h->d_red, sizeof(float) * ((size_t)h->R + 1)));
+    CKH(cudaMalloc(&h->d_U, sizeof(float) * (size_t)h->R));
+    CKH(cudaMalloc(&h->d_Uprev, sizeof(float) * (size_t)h->R));
+    CKH(cudaMalloc(&h->d_next, sizeof(float) * kMaxAct));
+    CKH(cudaMalloc(&h->d_prob, sizeof(ProblemDev)));
+    CKH(cudaMalloc(&h->d_ctl, sizeof(CtlDev)));
+    CKH(cudaMallocHost(&h->h_stage, sizeof(float) * kStageSlots * 2 * kMaxAct));
+    CKH(cudaMallocHost(&h->h_next, sizeof(float) * kMaxAct));
+    // eps zeroed like the reference's cudaMemset(_e, 0) (src/point_mass.cu:69): keeps the
+    // pad columns finite and defines injected-noise mode before the first mppi_set_noise.
+    CKH(cudaMemsetAsync(h->d_eps, 0, eps_bytes, h->stream));
+    CKH(cudaMemsetAsync(h->d_S, 0, sizeof(float) * (size_t)c.k_pad, h->stream));
+    CKH(cudaMemsetAsync(h->d_wt, 0, sizeof(float) * (size_t)c.k_pad, h->stream));
+    CKH(cudaMemsetAsync(h->d_partials, 0, sizeof(float) * (size_t)h->R * c.avg_gpad, h->stream));
+    CKH(cudaMemsetAsync(h->d_U, 0, sizeof(float) * (size_t)h->R, h->stream));
+    CKH(cudaMemsetAsync(h->d_Uprev, 0, sizeof(float) * (size_t)h->R, h->stream));
+    CKH(cudaMemsetAsync(h->d_red, 0, sizeof(float) * ((size_t)h->R + 1), h->stream));
+    CKH(launch_clear_ctl(c, h->d_ctl));
+    for (auto &e : h->ev) CKH(cudaEventCreate(&e));
+    CKH(cudaEventCreate(&h->t0));
+    CKH(cudaEventCreate(&h->t1));
+    CKH(configure_kernels(c));
+#undef CKH
+
+    // problem constants: gains as the reference forms them (src/point_mass.cu:46-51)
+    ProblemDev &pd = h->h_prob;
+    memset(&pd, 0, sizeof pd);
+    const float dt = p.dt;
+    const float dt2 = dt * dt;
+    pd.g[0] = 1.0f; pd.g[1] = dt; pd.g[2] = 0.0f; pd.g[3] = 1.0f;
+    pd.b[0] = (float)((double)dt2 / 2.0);
+    pd.b[1] = dt;
+    pd.lambda = p.lambda;
+    pd.neg_inv_lambda = -(1 / p.lambda);
+    for (int a = 0; a < p.act_dim; ++a) {
+        pd.inv_s[a] = p.inv_sigma[a];
+        pd.sigma[a] = p.sigma[a];
+        pd.init_act[a] = p.init_act[a];
+        pd.max_act[a] = p.max_act[a];
+    }
+    if ((rc = upload_problem(h)) != MPPI_OK) { mppi_destroy(h); return rc; }
+    if ((rc = encode_tmap(h)) != MPPI_OK) { mppi_destroy(h); return rc; }
+
+    if (multi(h)) {
+        std::string err;
+        if (!h->comm.init(p.rank, p.world_size, p.comm_id, err)) {
+            rc = fail(MPPI_ERR_COMM, "%s", err.c_str());
+            mppi_destroy(h);
+            return rc;
+        }
+    }
+    if (p.verbose)
+        fprintf(stderr, "[mppi_b200] device %d (%s, %d SMs) shard %d/%d: K_local=%lld (offset %lld, pad %lld) "
+                        "T=%d A=%d eps=%.1f MB avg_grid=%d\n",
+                p.device, prop.name, c.num_sms, p.rank, p.world_size, (long long)c.k_local,
+                (long long)c.k_offset, (long long)c.k_pad, p.horizon, p.act_dim,
+                eps_bytes / 1048576.0, c.avg_grid);
+    *out = h;
+    return MPPI_OK;
+}
+
+int mppi_shard_range(int64_t samples, int rank, int world_size, int64_t *k_begin, int64_t *k_end)
+{
+    if (samples < 1 || world_size < 1 || rank < 0 || rank >= world_size || !k_begin || !k_end)
+        return fail(MPPI_ERR_INVALID, "mppi_shard_range: bad arguments");
+    const int64_t quads = (samples + 3) / 4;
+    const int64_t q0 = quads * rank / world_size;
+    const int64_t q1 = quads * (rank + 1) / world_size;
+    *k_begin = 4 * q0;
+    *k_end = (4 * q1 < samples) ? 4 * q1 : samples;
+    return MPPI_OK;
+}
+
+int mppi_local_samples(mppi_handle *h, int64_t *k_local, int64_t *k_offset)
+{
+    if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+    if (k_local) *k_local = h->ctx.k_local;
+    if (k_offset) *k_offset = h->ctx.k_offset;
+    return MPPI_OK;
+}
+
+int mppi_set_problem(mppi_handle *h, const float *x0, const float *u, const float *goal,
+                     const float *w)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!x0 || !u || !goal || !w) return fail(MPPI_ERR_INVALID, "null argument");
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < h->S; ++i) {
+        h->h_prob.x0[i] = x0[i];
+        h->h_prob.goal[i] = goal[i];
+        h->h_prob.w[i] = w[i];
+    }
+    if ((rc = upload_problem(h)) != MPPI_OK) return rc;
+    CK(cudaMemcpyAsync(h->d_U, u, sizeof(float) * h->R, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_Uprev, u, sizeof(float) * h->R, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->problem_set = true;
+    return MPPI_OK;
+}
+
+int mppi_set_u(mppi_handle *h, const float *u)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!u) return fail(MPPI_ERR_INVALID, "null argument");
+    CK(cudaMemcpyAsync(h->d_U, u, sizeof(float) * h->R, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_set_state(mppi_handle *h, const float *x)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!x) return fail(MPPI_ERR_INVALID, "null argument");
+    float *slot = h->h_stage + (size_t)h->stage_slot * 2 * kMaxAct;
+    h->stage_slot = (h->stage_slot + 1) % kStageSlots;
+    for (int i = 0; i < h->S; ++i) { slot[i] = x[i]; h->h_prob.x0[i] = x[i]; }
+    CK(cudaMemcpyAsync(reinterpret_cast<char *>(h->d_prob) + offsetof(ProblemDev, x0), slot,
+                       sizeof(float) * h->S, cudaMemcpyHostToDevice, h->stream));
+    return MPPI_OK;
+}
+
+int mppi_step_enqueue(mppi_handle *h)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!h->problem_set) return fail(MPPI_ERR_STATE, "mppi_step before mppi_set_problem");
+    const bool sample = !h->injected;
+    const int which = sample ? 0 : 1;
+    if (h->profiling || (h->p.flags & MPPI_FLAG_NO_GRAPH)) {
+        rc = enqueue_chain(h, sample, h->profiling ? h->ev : nullptr);
+        if (rc) return rc;
+        if (h->profiling) {
+            CK(cudaStreamSynchronize(h->stream));
+            // event i+1 closes stage i of {sample, rollout, comm_min, weights, average,
+            // (fold+)comm_sum, finalize(+D2H)}
+            for (int i = 0; i < MPPI_K_COUNT; ++i) {
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+                const bool ran = (i == MPPI_K_SAMPLE) ? (sample && !fused(h))
+                               : (i == MPPI_K_COMM_MIN || i == MPPI_K_COMM_SUM) ? multi(h) : true;
+                if (ran) { h->ms_sum[i] += ms; h->launches[i] += 1; }
+            }
+        }
+    } else {
+        if (!h->graph_exec[which] && (rc = build_graph(h, which)) != MPPI_OK) return rc;
+        CK(cudaGraphLaunch(h->graph_exec[which], h->stream));
+    }
+    h->total_launches += kernels_per_step(h, sample);
+    h->pending = true;
+    return MPPI_OK;
+}
+
+int mppi_step_wait(mppi_handle *h, float *next_act)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->pending = false;
+    if (next_act)
+        for (int a = 0; a < h->p.act_dim; ++a) next_act[a] = h->h_next[a];
+    return MPPI_OK;
+}
+
+int mppi_step(mppi_handle *h, float *next_act)
+{
+    int rc = mppi_step_enqueue(h);
+    if (rc) return rc;
+    return mppi_step_wait(h, next_act);
+}
+
+int mppi_get_u(mppi_handle *h, float *u)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!u) return fail(MPPI_ERR_INVALID, "null argument");
+    CK(cudaMemcpyAsync(u, h->d_U, sizeof(float) * h->R, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_get_step_info(mppi_handle *h, mppi_step_info *info)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!info) return fail(MPPI_ERR_INVALID, "null argument");
+    CtlDev ctl;
+    CK(cudaMemcpyAsync(&ctl, h->d_ctl, sizeof ctl, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    info->beta = ordered_to_float((uint32_t)(ctl.last_key >> 32));
+    info->argmin = (int64_t)(ctl.last_key & 0xffffffffull);
+    info->eta = ctl.eta;
+    info->step = ctl.step;
+    if (ctl.last_key == kMinKeyInit) { info->beta = NAN; info->argmin = -1; }
+    return MPPI_OK;
+}
+
+int mppi_get_info(mppi_handle *h, float *x, float *u, float *e, float *cost, float *beta,
+                  float *nabla, float *weight)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    const LaunchCtx &c = h->ctx;
+    CK(cudaStreamSynchronize(h->stream));
+    mppi_step_info info;
+    if ((rc = mppi_get_step_info(h, &info)) != MPPI_OK) return rc;
+    if (beta) *beta = info.beta;
+    if (nabla) *nabla = info.eta;
+    if (u) CK(cudaMemcpyAsync(u, h->d_U, sizeof(float) * h->R, cudaMemcpyDeviceToHost, h->stream));
+    if (cost)
+        CK(cudaMemcpyAsync(cost, h->d_S, sizeof(float) * (size_t)c.k_local, cudaMemcpyDeviceToHost,
+                           h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+
+    float *scratch = nullptr;
+    auto release = [&]() { if (scratch) { cudaFree(scratch); scratch = nullptr; } };
+#define CKS(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            release();                                                                    \
+            return fail(MPPI_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,       \
+                        cudaGetErrorString(e__));                                         \
+        }                                                                                 \
+    } while (0)
+    if (weight) {
+        CKS(cudaMalloc(&scratch, sizeof(float) * (size_t)c.k_local));
+        CKS(launch_norm_weights(c, h->d_S, h->p.lambda, info.beta, info.eta, scratch));
+        CKS(cudaMemcpyAsync(weight, scratch, sizeof(float) * (size_t)c.k_local,
+                            cudaMemcpyDeviceToHost, h->stream));
+        CKS(cudaStreamSynchronize(h->stream));
+        release();
+    }
+    if (e) {
+        const size_t n = (size_t)c.k_local * h->R;
+        CKS(cudaMalloc(&scratch, sizeof(float) * n));
+        CKS(launch_to_reference(c, h->d_eps, scratch));
+        CKS(cudaMemcpyAsync(e, scratch, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+        CKS(cudaStreamSynchronize(h->stream));
+        release();
+    }
+    if (x) {
+        const size_t n = (size_t)c.k_local * (h->p.horizon + 1) * h->S;
+        CKS(cudaMalloc(&scratch, sizeof(float) * n));
+        CKS(launch_trajectories(c, h->d_eps, h->d_Uprev, h->d_prob, scratch));
+        CKS(cudaMemcpyAsync(x, scratch, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+        CKS(cudaStreamSynchronize(h->stream));
+        release();
+    }
+#undef CKS
+    return MPPI_OK;
+}
+
+int mppi_set_noise_mode(mppi_handle *h, int injected)
+{
+    if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+    h->injected = injected != 0;
+    return MPPI_OK;
+}
+
+int mppi_set_noise(mppi_handle *h, const float *e)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!e) return fail(MPPI_ERR_INVALID, "null argument");
+    const LaunchCtx &c = h->ctx;
+    const size_t n = (size_t)c.k_local * h->R;
+    float *scratch = nullptr;
+    CK(cudaMalloc(&scratch, sizeof(float) * n));
+    cudaError_t err = cudaMemcpyAsync(scratch, e, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream);
+    if (err == cudaSuccess) err = launch_to_internal(c, scratch, h->d_eps);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+    cudaFree(scratch);
+    if (err != cudaSuccess)
+        return fail(MPPI_ERR_CUDA, "mppi_set_noise -> %s", cudaGetErrorString(err));
+    h->injected = true;
+    return MPPI_OK;
+}
+
+int mppi_sample_only(mppi_handle *h, uint64_t step)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    CK(launch_sample(h->ctx, h->d_eps, h->d_prob, h->d_ctl, true, step));
+    CK(cudaStreamSynchronize(h->stream));
+    h->total_launches += 1;
+    return MPPI_OK;
+}
+
+int mppi_timer_start(mppi_handle *h)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->t0, h->stream));
+    return MPPI_OK;
+}
+
+int mppi_timer_stop(mppi_handle *h, float *elapsed_ms)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->t1, h->stream));
+    CK(cudaEventSynchronize(h->t1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->t0, h->t1));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return MPPI_OK;
+}
+
+int mppi_set_profiling(mppi_handle *h, int enabled)
+{
+    if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+    h->profiling = enabled != 0;
+    return MPPI_OK;
+}
+
+int mppi_get_kernel_times(mppi_handle *h, double *ms_sum, int64_t *launches)
+{
+    if (!h) return fail(MPPI_ERR_INVALID, "null handle");
+    for (int i = 0; i < MPPI_K_COUNT; ++i) {
+        if (ms_sum) ms_sum[i] = h->ms_sum[i];
+        if (launches) launches[i] = h->launches[i];
+        h->ms_sum[i] = 0.0;
+        h->launches[i] = 0;
+    }
+    return MPPI_OK;
+}
+
+int mppi_get_launch_count(mppi_handle *h, int64_t *launches)
+{
+    if (!h || !launches) return fail(MPPI_ERR_INVALID, "null argument");
+    *launches = h->total_launches;
+    return MPPI_OK;
+}
+
+}  // extern "C"

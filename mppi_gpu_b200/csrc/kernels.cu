@@ -1,0 +1,739 @@
+// kernels.cu -- hand-written sm_100a kernels of one MPPI control step.
+//
+// Data layout in HBM (per shard, all float32):
+//   eps      [R = T*A rows][k_pad]   K-minor: row r = t*A+a holds that perturbation component
+//                                    of every sample; k_pad = K_local rounded up to 256.
+//                                    (The reference keeps [K][T][A], src/point_mass.cu:784,
+//                                    which makes every per-sample access a T*A-float stride.)
+//   S, wt    [k_pad]                 rollout costs and unnormalised weights
+//   partials [R][gpad]               per-CTA partial sums of the weighted average
+//   U, U_prev[T*A]
+//
+// Kernel chain of a control step (reference: PointMassModel::get_act, src/point_mass.cu:129-203):
+//   sample -> rollout(+min) -> weights(+eta partials) -> average -> finalize
+#include "kernels.cuh"
+#include "philox.cuh"
+
+namespace mppi {
+
+// =================================================================================
+// (1) sampling: replaces curand_normal in PointMassModelGpu::step
+//     (src/point_mass_gpu.cu:85-90).  HBM-write bound: 4*K*T*A bytes.
+// =================================================================================
+constexpr int kSampleRowsPerThread = 4;
+
+template <int A>
+__global__ void __launch_bounds__(256)
+sample_kernel(float *__restrict__ eps, size_t ld, int rows, const ProblemDev *__restrict__ prob,
+              const CtlDev *__restrict__ ctl, unsigned long long k_offset, unsigned long long seed,
+              int use_step_override, unsigned long long step_override)
+{
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // local quad
+    if (4 * q >= ld) return;
+    const unsigned long long step = use_step_override ? step_override : ctl->step;
+    const uint32_t qg = (uint32_t)((k_offset >> 2) + q);                 // global quad
+    float sig[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) sig[a] = prob->sigma[a];
+
+    const int r0 = blockIdx.y * kSampleRowsPerThread;
+#pragma unroll
+    for (int j = 0; j < kSampleRowsPerThread; ++j) {
+        const int r = r0 + j;
+        if (r < rows) {
+            float4 n = normal4(qg, (uint32_t)r, step, seed);
+            float s = sig[0];
+#pragma unroll
+            for (int a = 1; a < A; ++a) s = (r % A == a) ? sig[a] : s;
+            n.x *= s; n.y *= s; n.z *= s; n.w *= s;
+            stg_f4(eps + (size_t)r * ld + 4 * q, n);
+        }
+    }
+}
+
+// =================================================================================
+// (2) fused rollout: PointMassModelGpu::run/step (src/point_mass_gpu.cu:82-121) with
+//     Cost::step_cost / final_cost (src/cost.cu:42-64) accumulated in registers.
+//     One thread integrates FOUR consecutive samples (one float4 of every eps row), U[t]
+//     and U[t]*inv_s are staged once per CTA in shared memory, the trajectory is never
+//     written.  Epilogue: warp-shuffle + CTA min of the packed (cost, index) key and one
+//     atomicMin per CTA (replaces min_red, src/point_mass.cu:533-575).
+//
+//     Arithmetic.  The gains are structurally {1,dt,0,1}/{dt^2/2,dt} (src/point_mass.cu:46-51)
+//     so g0*p == p and g2*p + g3*v == v exactly.  STRICT rounds every product and sum
+//     separately in source order (== the reference's host build, bit-for-bit vs
+//     oracle ORACLE_ARITH_STRICT); otherwise the fused operations are exactly those nvcc
+//     -fmad=true forms for the reference's device build (== ORACLE_ARITH_FMA).
+// =================================================================================
+template <int A, bool STRICT>
+struct PointMass {
+    float dt, b0, b1, lambda;
+    float goal[2 * A], w[2 * A];
+
+    __device__ __forceinline__ void load(const ProblemDev *__restrict__ p)
+    {
+        dt = p->g[1]; b0 = p->b[0]; b1 = p->b[1]; lambda = p->lambda;
+#pragma unroll
+        for (int i = 0; i < 2 * A; ++i) { goal[i] = p->goal[i]; w[i] = p->w[i]; }
+    }
+
+    // state cost  sum_i (x_i-g_i)*w_i*(x_i-g_i)  added onto res in index order
+    __device__ __forceinline__ float state_cost(const float (&x)[2 * A], float res) const
+    {
+#pragma unroll
+        for (int i = 0; i < 2 * A; ++i) {
+            const float d = __fsub_rn(x[i], goal[i]);
+            if (STRICT) res = __fadd_rn(res, __fmul_rn(__fmul_rn(d, w[i]), d));
+            else        res = __fmaf_rn(__fmul_rn(d, w[i]), d, res);
+        }
+        return res;
+    }
+
+    // one step: x <- f(x, u+e);  c += step_cost(x_new, u, e)
+    __device__ __forceinline__ void step(float (&x)[2 * A], float &c, const float (&u)[A],
+                                         const float (&ui)[A], const float (&e)[A]) const
+    {
+        float res = 0.0f;
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            const float ue = __fadd_rn(u[i], e[i]);
+            const float p = x[i], v = x[i + A];
+            if (STRICT) {
+                x[i]     = __fadd_rn(__fadd_rn(p, __fmul_rn(dt, v)), __fmul_rn(b0, ue));
+                x[i + A] = __fadd_rn(v, __fmul_rn(b1, ue));
+                res = __fadd_rn(res, __fmul_rn(ui[i], e[i]));
+            } else {
+                x[i]     = __fmaf_rn(b0, ue, __fadd_rn(p, __fmul_rn(dt, v)));
+                x[i + A] = __fmaf_rn(b1, ue, v);
+                res = __fmaf_rn(ui[i], e[i], res);
+            }
+        }
+        res = __fmul_rn(res, lambda);
+        res = state_cost(x, res);
+        c = __fadd_rn(c, res);
+    }
+};
+
+template <int A, bool STRICT, bool FUSED>
+__global__ void __launch_bounds__(256)
+rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
+               const float *__restrict__ U, const ProblemDev *__restrict__ prob,
+               float *__restrict__ S, CtlDev *__restrict__ ctl, unsigned long long k_offset,
+               unsigned long long seed)
+{
+    extern __shared__ float smem_f[];
+    float *sU  = smem_f;            // U[t][a]
+    float *sUi = smem_f + T * A;    // U[t][a] * inv_s[a]   (src/cost.cu:46)
+    __shared__ unsigned long long s_key[8];
+
+    for (int i = threadIdx.x; i < T * A; i += blockDim.x) {
+        const float u = U[i];
+        sU[i]  = u;
+        sUi[i] = __fmul_rn(u, prob->inv_s[i % A]);
+    }
+    __syncthreads();
+
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long key = kMinKeyInit;
+
+    if (4 * q < ld) {
+        PointMass<A, STRICT> m;
+        m.load(prob);
+        float x[4][2 * A];
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 2 * A; ++i) x[j][i] = prob->x0[i];
+
+        float sig[A];
+        unsigned long long step = 0;
+        uint32_t qg = 0;
+        if (FUSED) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) sig[a] = prob->sigma[a];
+            step = ctl->step;
+            qg = (uint32_t)((k_offset >> 2) + q);
+        }
+
+        float *ep = eps + 4 * q;
+#pragma unroll 4
+        for (int t = 0; t < T; ++t) {
+            float4 e4[A];
+            float u[A], ui[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const int r = t * A + a;
+                if (FUSED) {
+                    float4 n = normal4(qg, (uint32_t)r, step, seed);
+                    n.x *= sig[a]; n.y *= sig[a]; n.z *= sig[a]; n.w *= sig[a];
+                    stg_f4(ep + (size_t)r * ld, n);
+                    e4[a] = n;
+                } else {
+                    e4[a] = ldg_stream_f4(ep + (size_t)r * ld);
+                }
+                u[a]  = sU[r];
+                ui[a] = sUi[r];
+            }
+            float e[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) e[a] = e4[a].x;
+            m.step(x[0], c[0], u, ui, e);
+#pragma unroll
+            for (int a = 0; a < A; ++a) e[a] = e4[a].y;
+            m.step(x[1], c[1], u, ui, e);
+#pragma unroll
+            for (int a = 0; a < A; ++a) e[a] = e4[a].z;
+            m.step(x[2], c[2], u, ui, e);
+#pragma unroll
+            for (int a = 0; a < A; ++a) e[a] = e4[a].w;
+            m.step(x[3], c[3], u, ui, e);
+        }
+        // terminal cost on x[T] (charged on top of the last stage cost,
+        // src/point_mass_gpu.cu:116)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[j] = __fadd_rn(c[j], m.state_cost(x[j], 0.0f));
+
+        stg_f4(S + 4 * q, make_float4(c[0], c[1], c[2], c[3]));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long k = (long long)(4 * q) + j;
+            if (k < k_local) {
+                const unsigned long long kk =
+                    ((unsigned long long)float_to_ordered(c[j]) << 32) |
+                    (unsigned long long)(uint32_t)(k_offset + (unsigned long long)k);
+                key = kk < key ? kk : key;
+            }
+        }
+    }
+
+    key = warp_min_u64(key);
+    if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        key = threadIdx.x < (blockDim.x >> 5) ? s_key[threadIdx.x] : kMinKeyInit;
+        key = warp_min_u64(key);
+        if (threadIdx.x == 0 && key != kMinKeyInit) atomicMin(&ctl->min_key, key);
+    }
+}
+
+// =================================================================================
+// (3) weights: exp_red + sum_red (src/point_mass.cu:510-531, :628-666) in one pass.
+//     wt[k] = expf(-(1/lambda) * (S[k] - beta)); deterministic per-CTA eta partial.
+// =================================================================================
+__global__ void __launch_bounds__(256)
+weights_kernel(const float *__restrict__ S, long long k_local, long long k_pad,
+               const ProblemDev *__restrict__ prob, const CtlDev *__restrict__ ctl,
+               float *__restrict__ wt, float *__restrict__ eta_part)
+{
+    __shared__ float s_sum[8];
+    const float beta = ordered_to_float((uint32_t)(ctl->min_key >> 32));
+    const float nil = prob->neg_inv_lambda;
+    const long long k0 = 4ll * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k0 < k_pad) {
+        const float4 s4 = *reinterpret_cast<const float4 *>(S + k0);
+        w4.x = (k0 + 0 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(s4.x, beta))) : 0.0f;
+        w4.y = (k0 + 1 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(s4.y, beta))) : 0.0f;
+        w4.z = (k0 + 2 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(s4.z, beta))) : 0.0f;
+        w4.w = (k0 + 3 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(s4.w, beta))) : 0.0f;
+        *reinterpret_cast<float4 *>(wt + k0) = w4;
+    }
+
+    float s = (w4.x + w4.y) + (w4.z + w4.w);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < 8 ? s_sum[threadIdx.x] : 0.0f;
+        s = warp_sum(s);
+        if (threadIdx.x == 0) eta_part[blockIdx.x] = s;
+    }
+}
+
+// =================================================================================
+// (4) weighted average  num[r] = sum_k wt[k] * eps[r][k]
+//     (replaces the T x {update_act_kernel, sum_red_adim, copy_act} launches of
+//     PointMassModel::update_act, src/point_mass.cu:384-480, :828-926).
+//
+//     GEMV-shaped and HBM-bound (4*K*T*A bytes read once, one FMA per 4 bytes), so no
+//     tensor cores: a persistent, warp-specialised streaming reduction.  One CTA per SM;
+//     warp 8 is the TMA producer: per tile one cp.async.bulk.tensor.2d of a
+//     [kAvgTileR rows x 256 samples] eps box (40 KB) plus one 1 KB bulk copy of the matching
+//     weights, landing on an mbarrier; kAvgStages tiles are in flight per SM.  Warps 0-7
+//     consume: warp w owns the rows {w, w+8, ...} of every tile, each lane multiplies its 8
+//     samples of the row by the weights held in registers, the warp shuffle-reduces and lane 0
+//     accumulates the row sum in shared memory.  The tile -> CTA assignment is static, every
+//     row sum is formed in a fixed order, the per-CTA partials are written once at the end:
+//     bitwise reproducible.
+// =================================================================================
+size_t average_smem_bytes(int R)
+{
+    size_t tiles = (size_t)kAvgStages * kAvgTileR * kAvgTileK * sizeof(float);
+    size_t wts   = (size_t)kAvgStages * kAvgTileK * sizeof(float);
+    size_t rows  = (size_t)((R + 31) / 32 * 32) * sizeof(float);
+    size_t bars  = 2 * kAvgStages * sizeof(uint64_t);
+    return tiles + wts + rows + bars + 128;   // + alignment slack
+}
+
+__global__ void __launch_bounds__(kAvgThreads, 1)
+average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__restrict__ wt,
+               float *__restrict__ partials, int gpad, int rows, int nslab, int nchunk)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // 128-byte aligned carve-up (TMA destinations need 128 B)
+    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    float *s_tile = reinterpret_cast<float *>(base);                               // [stage][R][K]
+    float *s_wt   = s_tile + (size_t)kAvgStages * kAvgTileR * kAvgTileK;           // [stage][K]
+    float *s_row  = s_wt + (size_t)kAvgStages * kAvgTileK;                         // [rows32]
+    const int rows32 = (rows + 31) / 32 * 32;
+    uint64_t *full_bar  = reinterpret_cast<uint64_t *>(s_row + rows32);
+    uint64_t *empty_bar = full_bar + kAvgStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < rows32; i += blockDim.x) s_row[i] = 0.0f;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kAvgStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kAvgConsumerWarps);
+        }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    // static, balanced partition of the slab-major tile list
+    const long long ntiles = (long long)nslab * nchunk;
+    const long long t_begin = ntiles * blockIdx.x / gridDim.x;
+    const long long t_end   = ntiles * (blockIdx.x + 1) / gridDim.x;
+
+    constexpr uint32_t kTileBytes = kAvgTileR * kAvgTileK * sizeof(float);
+    constexpr uint32_t kWtBytes   = kAvgTileK * sizeof(float);
+
+    if (warp == kAvgConsumerWarps) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_eps);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = t_begin; t < t_end; ++t) {
+                const int slab  = (int)(t / nchunk);
+                const int chunk = (int)(t - (long long)slab * nchunk);
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full_bar[stage], kTileBytes + kWtBytes);
+                tma_load_2d(s_tile + (size_t)stage * kAvgTileR * kAvgTileK, &tmap_eps,
+                            slab * kAvgTileK, chunk * kAvgTileR, &full_bar[stage]);
+                bulk_load_1d(s_wt + (size_t)stage * kAvgTileK, wt + (size_t)slab * kAvgTileK,
+                             kWtBytes, &full_bar[stage]);
+                if (++stage == kAvgStages) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------ consumers ---------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long t = t_begin; t < t_end; ++t) {
+            const int slab  = (int)(t / nchunk);
+            const int chunk = (int)(t - (long long)slab * nchunk);
+            mbar_wait(&full_bar[stage], phase);
+            const float *tw = s_wt + (size_t)stage * kAvgTileK;
+            const float4 w0 = *reinterpret_cast<const float4 *>(tw + 4 * lane);
+            const float4 w1 = *reinterpret_cast<const float4 *>(tw + 128 + 4 * lane);
+            const float *tile = s_tile + (size_t)stage * kAvgTileR * kAvgTileK;
+            float acc[kAvgTileR / kAvgConsumerWarps];
+#pragma unroll
+            for (int rr = 0; rr < kAvgTileR / kAvgConsumerWarps; ++rr) {
+                const float *row = tile + (size_t)(warp + kAvgConsumerWarps * rr) * kAvgTileK;
+                const float4 e0 = *reinterpret_cast<const float4 *>(row + 4 * lane);
+                const float4 e1 = *reinterpret_cast<const float4 *>(row + 128 + 4 * lane);
+                float a = e0.x * w0.x;
+                a = fmaf(e0.y, w0.y, a);
+                a = fmaf(e0.z, w0.z, a);
+                a = fmaf(e0.w, w0.w, a);
+                a = fmaf(e1.x, w1.x, a);
+                a = fmaf(e1.y, w1.y, a);
+                a = fmaf(e1.z, w1.z, a);
+                a = fmaf(e1.w, w1.w, a);
+                acc[rr] = a;
+            }
+            // all shared-memory reads of this stage are done: hand the slot back early
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+#pragma unroll
+            for (int rr = 0; rr < kAvgTileR / kAvgConsumerWarps; ++rr) acc[rr] = warp_sum(acc[rr]);
+            if (lane == 0) {
+#pragma unroll
+                for (int rr = 0; rr < kAvgTileR / kAvgConsumerWarps; ++rr) {
+                    const int r = chunk * kAvgTileR + warp + kAvgConsumerWarps * rr;
+                    if (r < rows) s_row[r] += acc[rr];
+                }
+            }
+            if (++stage == kAvgStages) { stage = 0; phase ^= 1; }
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < rows; r += blockDim.x)
+        partials[(size_t)r * gpad + blockIdx.x] = s_row[r];
+}
+
+// =================================================================================
+// (5) finalize: fold the per-CTA partials and eta (replaces sum_red_adim,
+//     src/point_mass.cu:668-741), U += num/eta (copy_act, :756-761), next action = U[0,:]
+//     (:195), receding-horizon shift with repeat-last / init-act re-initialisation
+//     (shift_act, :805-824), step counter advance and min_key re-arm.  One CTA.
+//     Multi-shard: FOLD writes red[0..R-1] = num, red[R] = eta_local for the all-reduce;
+//     UPDATE consumes the reduced vector.
+// =================================================================================
+constexpr int kFinThreads = 1024;
+
+template <bool FOLD, bool UPDATE>
+__global__ void __launch_bounds__(kFinThreads)
+finalize_kernel(const float *__restrict__ partials, int gpad, int ncta,
+                const float *__restrict__ eta_part, int neta, float *__restrict__ red,
+                float *__restrict__ U, float *__restrict__ U_prev,
+                const ProblemDev *__restrict__ prob, CtlDev *__restrict__ ctl,
+                float *__restrict__ next_act, int T, int A, unsigned flags)
+{
+    extern __shared__ float s_u[];          // U_new [T*A]
+    __shared__ float s_red[32];
+    __shared__ float s_eta;
+    const int R = T * A;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (FOLD) {
+        // eta: strided per-thread serial sums, then a fixed-shape tree
+        float e = 0.0f;
+        for (int i = threadIdx.x; i < neta; i += kFinThreads) e += eta_part[i];
+        e = warp_sum(e);
+        if (lane == 0) s_red[warp] = e;
+        __syncthreads();
+        if (warp == 0) {
+            e = s_red[lane];
+            e = warp_sum(e);
+            if (lane == 0) { s_eta = e; red[R] = e; }
+        }
+        // rows: one warp per row, lanes stride over the CTA partials
+        for (int r = warp; r < R; r += kFinThreads / 32) {
+            const float *p = partials + (size_t)r * gpad;
+            float s = 0.0f;
+            for (int g = lane; g < ncta; g += 32) s += p[g];
+            s = warp_sum(s);
+            if (lane == 0) red[r] = s;
+        }
+        __syncthreads();
+    }
+    if (UPDATE) {
+        const float eta = FOLD ? s_eta : red[R];
+        for (int i = threadIdx.x; i < R; i += kFinThreads) {
+            const float u = U[i];
+            float un = u + red[i] / eta;
+            if (flags & MPPI_FLAG_CLAMP_ACTIONS) {
+                const float m = prob->max_act[i % A];
+                un = fminf(fmaxf(un, -m), m);
+            }
+            U_prev[i] = u;
+            s_u[i] = un;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < R; i += kFinThreads) {
+            float v;
+            if (i < R - A)                              v = s_u[i + A];
+            else if (flags & MPPI_FLAG_REINIT_INIT_ACT) v = prob->init_act[i - (R - A)];
+            else                                        v = s_u[i];
+            U[i] = v;
+        }
+        if (threadIdx.x < A) next_act[threadIdx.x] = s_u[threadIdx.x];
+        if (threadIdx.x == 0) {
+            ctl->eta = eta;
+            ctl->eta_local = FOLD ? s_eta : ctl->eta_local;
+            ctl->last_key = ctl->min_key;
+            ctl->min_key = kMinKeyInit;
+            ctl->step = ctl->step + 1;
+        }
+    } else if (FOLD) {
+        if (threadIdx.x == 0) ctl->eta_local = s_eta;
+    }
+}
+
+// =================================================================================
+// layout conversion (parity taps): reference [K][R]  <->  internal [R][k_pad]
+// =================================================================================
+__global__ void __launch_bounds__(256)
+to_internal_kernel(const float *__restrict__ e_ref, float *__restrict__ eps, long long k_local,
+                   size_t ld, int R)
+{
+    __shared__ float tile[32][33];
+    const long long kb = (long long)blockIdx.x * 32;
+    const int rb = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const long long k = kb + j;
+        const int r = rb + tx;
+        tile[j][tx] = (k < k_local && r < R) ? e_ref[(size_t)k * R + r] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int r = rb + j;
+        const long long k = kb + tx;
+        if (r < R && k < k_local) eps[(size_t)r * ld + k] = tile[tx][j];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+to_reference_kernel(const float *__restrict__ eps, float *__restrict__ e_ref, long long k_local,
+                    size_t ld, int R)
+{
+    __shared__ float tile[32][33];
+    const long long kb = (long long)blockIdx.x * 32;
+    const int rb = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int r = rb + j;
+        const long long k = kb + tx;
+        tile[j][tx] = (r < R && k < k_local) ? eps[(size_t)r * ld + k] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const long long k = kb + j;
+        const int r = rb + tx;
+        if (k < k_local && r < R) e_ref[(size_t)k * R + r] = tile[tx][j];
+    }
+}
+
+// =================================================================================
+// debug taps for get_inf (src/point_mass.cu:236-262)
+// =================================================================================
+// weights_kernel of the reference with its double literals (src/point_mass.cu:751)
+__global__ void __launch_bounds__(256)
+norm_weights_kernel(const float *__restrict__ S, long long k_local, float lambda, float beta,
+                    float eta, float *__restrict__ w_out)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k_local) return;
+    const double inv_eta = 1.0 / (double)eta;
+    const double nil = -(1.0 / (double)lambda);
+    const float diff = __fsub_rn(S[k], beta);
+    const float arg = (float)(nil * (double)diff);
+    w_out[k] = (float)(inv_eta * (double)expf(arg));
+}
+
+template <int A, bool STRICT>
+__global__ void __launch_bounds__(128)
+trajectories_kernel(const float *__restrict__ eps, size_t ld, long long k_local, int T,
+                    const float *__restrict__ U, const ProblemDev *__restrict__ prob,
+                    float *__restrict__ x_out)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k_local) return;
+    PointMass<A, STRICT> m;
+    m.load(prob);
+    float x[2 * A], c = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 2 * A; ++i) x[i] = prob->x0[i];
+    float *xo = x_out + (size_t)k * (T + 1) * 2 * A;
+#pragma unroll
+    for (int i = 0; i < 2 * A; ++i) xo[i] = x[i];
+    for (int t = 0; t < T; ++t) {
+        float u[A], ui[A], e[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            u[a] = U[t * A + a];
+            ui[a] = __fmul_rn(u[a], prob->inv_s[a]);
+            e[a] = eps[(size_t)(t * A + a) * ld + k];
+        }
+        m.step(x, c, u, ui, e);
+#pragma unroll
+        for (int i = 0; i < 2 * A; ++i) xo[(size_t)(t + 1) * 2 * A + i] = x[i];
+    }
+}
+
+__global__ void clear_ctl_kernel(CtlDev *ctl)
+{
+    ctl->min_key = kMinKeyInit;
+    ctl->last_key = kMinKeyInit;
+    ctl->step = 0;
+    ctl->eta = 0.0f;
+    ctl->eta_local = 0.0f;
+}
+
+// =================================================================================
+// launch wrappers
+// =================================================================================
+#define MPPI_DISPATCH_A(A_, ...)                                        \
+    switch (A_) {                                                       \
+        case 1: { constexpr int kA = 1; __VA_ARGS__; break; }           \
+        case 2: { constexpr int kA = 2; __VA_ARGS__; break; }           \
+        case 3: { constexpr int kA = 3; __VA_ARGS__; break; }           \
+        case 4: { constexpr int kA = 4; __VA_ARGS__; break; }           \
+        default: return cudaErrorInvalidValue;                          \
+    }
+
+cudaError_t launch_sample(const LaunchCtx &c, float *eps, const ProblemDev *prob, const CtlDev *ctl,
+                          bool use_step_override, unsigned long long step_override)
+{
+    const size_t quads = (size_t)c.k_pad / 4;
+    dim3 grid((unsigned)((quads + 255) / 256),
+              (unsigned)((c.rows + kSampleRowsPerThread - 1) / kSampleRowsPerThread));
+    MPPI_DISPATCH_A(c.act_dim,
+        sample_kernel<kA><<<grid, 256, 0, c.stream>>>(eps, (size_t)c.k_pad, c.rows, prob, ctl,
+                                                      (unsigned long long)c.k_offset, c.seed,
+                                                      use_step_override ? 1 : 0, step_override));
+    return cudaGetLastError();
+}
+
+template <int A, bool STRICT, bool FUSED>
+static cudaError_t launch_rollout_t(const LaunchCtx &c, float *eps, const float *U,
+                                    const ProblemDev *prob, float *S, CtlDev *ctl)
+{
+    const size_t quads = (size_t)c.k_pad / 4;
+    const unsigned grid = (unsigned)((quads + 255) / 256);
+    const size_t smem = 2 * sizeof(float) * (size_t)c.rows;
+    auto kern = rollout_kernel<A, STRICT, FUSED>;
+    kern<<<grid, 256, smem, c.stream>>>(eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U,
+                                        prob, S, ctl, (unsigned long long)c.k_offset, c.seed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rollout(const LaunchCtx &c, float *eps, const float *U, const ProblemDev *prob,
+                           float *S, CtlDev *ctl, bool fused)
+{
+    MPPI_DISPATCH_A(c.act_dim,
+        if (c.strict) {
+            return fused ? launch_rollout_t<kA, true, true>(c, eps, U, prob, S, ctl)
+                         : launch_rollout_t<kA, true, false>(c, eps, U, prob, S, ctl);
+        } else {
+            return fused ? launch_rollout_t<kA, false, true>(c, eps, U, prob, S, ctl)
+                         : launch_rollout_t<kA, false, false>(c, eps, U, prob, S, ctl);
+        });
+    return cudaSuccess;
+}
+
+cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev *prob,
+                           const CtlDev *ctl, float *wt, float *eta_part)
+{
+    weights_kernel<<<c.weights_blocks, 256, 0, c.stream>>>(S, (long long)c.k_local,
+                                                           (long long)c.k_pad, prob, ctl, wt,
+                                                           eta_part);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *wt,
+                           float *partials)
+{
+    const size_t smem = average_smem_bytes(c.rows);
+    const int nslab = (int)(c.k_pad / kAvgTileK);
+    const int nchunk = (c.rows + kAvgTileR - 1) / kAvgTileR;
+    average_kernel<<<c.avg_grid, kAvgThreads, smem, c.stream>>>(tmap_eps, wt, partials, c.avg_gpad,
+                                                                c.rows, nslab, nchunk);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const LaunchCtx &c, bool fold, bool update, const float *partials,
+                            const float *eta_part, float *red, float *U, float *U_prev,
+                            const ProblemDev *prob, CtlDev *ctl, float *next_act, unsigned flags)
+{
+    const size_t smem = sizeof(float) * (size_t)c.rows;
+#define MPPI_FIN_ARGS partials, c.avg_gpad, c.avg_grid, eta_part, c.weights_blocks, red, U, U_prev, \
+                      prob, ctl, next_act, c.horizon, c.act_dim, flags
+    if (fold && update)
+        finalize_kernel<true, true><<<1, kFinThreads, smem, c.stream>>>(MPPI_FIN_ARGS);
+    else if (fold)
+        finalize_kernel<true, false><<<1, kFinThreads, smem, c.stream>>>(MPPI_FIN_ARGS);
+    else if (update)
+        finalize_kernel<false, true><<<1, kFinThreads, smem, c.stream>>>(MPPI_FIN_ARGS);
+    else
+        return cudaErrorInvalidValue;
+#undef MPPI_FIN_ARGS
+    return cudaGetLastError();
+}
+
+cudaError_t launch_to_internal(const LaunchCtx &c, const float *e_ref, float *eps)
+{
+    dim3 grid((unsigned)((c.k_local + 31) / 32), (unsigned)((c.rows + 31) / 32));
+    to_internal_kernel<<<grid, 256, 0, c.stream>>>(e_ref, eps, (long long)c.k_local,
+                                                   (size_t)c.k_pad, c.rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_to_reference(const LaunchCtx &c, const float *eps, float *e_ref)
+{
+    dim3 grid((unsigned)((c.k_local + 31) / 32), (unsigned)((c.rows + 31) / 32));
+    to_reference_kernel<<<grid, 256, 0, c.stream>>>(eps, e_ref, (long long)c.k_local,
+                                                    (size_t)c.k_pad, c.rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_norm_weights(const LaunchCtx &c, const float *S, float lambda, float beta,
+                                float eta, float *w_out)
+{
+    const unsigned grid = (unsigned)((c.k_local + 255) / 256);
+    norm_weights_kernel<<<grid, 256, 0, c.stream>>>(S, (long long)c.k_local, lambda, beta, eta,
+                                                    w_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trajectories(const LaunchCtx &c, const float *eps, const float *U_prev,
+                                const ProblemDev *prob, float *x_out)
+{
+    const unsigned grid = (unsigned)((c.k_local + 127) / 128);
+    MPPI_DISPATCH_A(c.act_dim,
+        if (c.strict)
+            trajectories_kernel<kA, true><<<grid, 128, 0, c.stream>>>(
+                eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U_prev, prob, x_out);
+        else
+            trajectories_kernel<kA, false><<<grid, 128, 0, c.stream>>>(
+                eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U_prev, prob, x_out));
+    return cudaGetLastError();
+}
+
+// Per-device one-time opt-in to large dynamic shared memory (called from mppi_create).
+template <int A>
+static cudaError_t configure_rollout(int smem)
+{
+    cudaError_t e;
+    e = cudaFuncSetAttribute(rollout_kernel<A, true, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rollout_kernel<A, true, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rollout_kernel<A, false, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(rollout_kernel<A, false, false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+cudaError_t configure_kernels(const LaunchCtx &c)
+{
+    cudaError_t e = cudaFuncSetAttribute(average_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)average_smem_bytes(c.rows));
+    if (e != cudaSuccess) return e;
+    const int fin = (int)(sizeof(float) * (size_t)c.rows);
+    if (fin > 48 * 1024) {
+        e = cudaFuncSetAttribute(finalize_kernel<true, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(finalize_kernel<false, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
+        if (e != cudaSuccess) return e;
+    }
+    const int ro = (int)(2 * sizeof(float) * (size_t)c.rows);
+    if (ro > 48 * 1024) {
+        MPPI_DISPATCH_A(c.act_dim, e = configure_rollout<kA>(ro));
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_clear_ctl(const LaunchCtx &c, CtlDev *ctl)
+{
+    clear_ctl_kernel<<<1, 1, 0, c.stream>>>(ctl);
+    return cudaGetLastError();
+}
+
+}  // namespace mppi

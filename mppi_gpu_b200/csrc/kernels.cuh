@@ -1,0 +1,73 @@
+// kernels.cuh -- launch interface of the sm_100a kernels (definitions in kernels.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace mppi {
+
+// Tile geometry of the weighted-average kernel (part 4).
+constexpr int kAvgTileK    = 256;   // samples per tile (TMA box inner dim, 1 KB per row)
+constexpr int kAvgTileR    = 40;    // eps rows per tile: divides T*A = 200/400/600
+constexpr int kAvgStages   = 4;     // TMA pipeline depth: 4 x 41 KB in flight per SM
+constexpr int kAvgConsumerWarps = 8;
+constexpr int kAvgThreads  = (kAvgConsumerWarps + 1) * 32;   // + 1 producer warp
+constexpr int kKPad        = 256;   // eps leading dimension is a multiple of this
+constexpr int kWeightsBlockSamples = 1024;   // samples per CTA in the weights kernel
+
+size_t average_smem_bytes(int R);
+
+struct LaunchCtx {
+    cudaStream_t stream;
+    int act_dim;           // A
+    int horizon;           // T
+    int rows;              // R = T*A
+    int64_t k_local;       // samples of this shard
+    int64_t k_pad;         // leading dimension of eps / weights (multiple of kKPad)
+    int64_t k_offset;      // global index of local sample 0 (multiple of 4)
+    unsigned long long seed;
+    bool strict;           // MPPI_FLAG_STRICT_ARITH
+    int  num_sms;
+    int  avg_grid;         // CTAs of the averaging kernel
+    int  avg_gpad;         // leading dimension of the per-CTA partials (multiple of 32)
+    int  weights_blocks;   // CTAs of the weights kernel == number of eta partials
+};
+
+// (1) eps[r][k] = sigma[a] * N(0,1), Philox counter (k/4, r, step)
+cudaError_t launch_sample(const LaunchCtx &c, float *eps, const ProblemDev *prob, const CtlDev *ctl,
+                          bool use_step_override, unsigned long long step_override);
+
+// (2) S[k] = rollout cost; block min -> atomicMin(ctl->min_key).  fused: also samples eps.
+cudaError_t launch_rollout(const LaunchCtx &c, float *eps, const float *U, const ProblemDev *prob,
+                           float *S, CtlDev *ctl, bool fused_sampling);
+
+// (3) wt[k] = expf(-(1/lambda)(S[k]-beta)), eta_part[block] = sum
+cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev *prob,
+                           const CtlDev *ctl, float *wt, float *eta_part);
+
+// (4) partials[r][cta] = sum_{k in cta's tiles} wt[k] * eps[r][k]
+cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *wt,
+                           float *partials);
+
+// (5) fold partials (+eta) -> red[0..R] ; update U, shift, next_act, advance step
+cudaError_t launch_finalize(const LaunchCtx &c, bool fold, bool update, const float *partials,
+                            const float *eta_part, float *red, float *U, float *U_prev,
+                            const ProblemDev *prob, CtlDev *ctl, float *next_act, unsigned flags);
+
+// layout conversion between the reference's [K][T*A] and the internal K-minor [T*A][k_pad]
+cudaError_t launch_to_internal(const LaunchCtx &c, const float *e_ref, float *eps);
+cudaError_t launch_to_reference(const LaunchCtx &c, const float *eps, float *e_ref);
+
+// debug taps (get_inf): normalised weights with the reference's mixed-precision formula,
+// and the trajectories x[K][T+1][S] recomputed from eps and the pre-update U.
+cudaError_t launch_norm_weights(const LaunchCtx &c, const float *S, float lambda, float beta,
+                                float eta, float *w_out);
+cudaError_t launch_trajectories(const LaunchCtx &c, const float *eps, const float *U_prev,
+                                const ProblemDev *prob, float *x_out);
+
+// reset the control block (min key armed, step 0)
+cudaError_t launch_clear_ctl(const LaunchCtx &c, CtlDev *ctl);
+
+// one-time per-device opt-in to large dynamic shared memory for the shapes in c
+cudaError_t configure_kernels(const LaunchCtx &c);
+
+}  // namespace mppi

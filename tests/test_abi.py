@@ -1,0 +1,108 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports
+every symbol include/mppi_b200.h declares, and fails loudly (no fallback) when no
+device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from mppi_gpu_b200 import capi
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "mppi_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mppi_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    names = _declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"libmppi_b200.so does not export {n}"
+    assert sorted(capi.EXPORTS) == names, "capi.EXPORTS out of sync with the header"
+
+
+def test_abi_version_and_struct_layout():
+    lib = capi.load()
+    assert lib.mppi_abi_version() == 1
+    p = capi.MppiParams()
+    assert lib.mppi_params_default(C.byref(p)) == 0
+    # the C side wrote sizeof(mppi_params): the ctypes mirror must agree
+    assert p.struct_size == C.sizeof(capi.MppiParams)
+    # reference-compatible preset (src/point_mass.cu:53-54, src/point_mass_gpu.cu:58-61,86)
+    assert p.lambda_ == 1.0 and p.world_size == 1 and p.comm == capi.COMM_NONE
+    assert all(abs(p.sigma[a] - 0.025) < 1e-9 for a in range(capi.MAX_ACT))
+    assert all(p.inv_sigma[a] == 1.0 for a in range(capi.MAX_ACT))
+    assert p.flags == 0 and p.seed == 0
+
+
+def test_kernel_names():
+    lib = capi.load()
+    names = [lib.mppi_kernel_name(i).decode() for i in range(capi.K_COUNT)]
+    assert names == ["sample", "rollout", "comm_min", "weights", "average", "comm_sum", "finalize"]
+
+
+def test_shard_ranges_tile_the_samples():
+    for K in (1, 3, 4, 5, 1000, 10007, 1000000, 1000003):
+        for W in (1, 2, 3, 4, 8):
+            if (K + 3) // 4 < W:
+                continue
+            edges = [capi.shard_range(K, r, W) for r in range(W)]
+            assert edges[0][0] == 0 and edges[-1][1] == K
+            for (b0, e0), (b1, e1) in zip(edges, edges[1:]):
+                assert e0 == b1 and b1 % 4 == 0          # whole Philox quads
+            sizes = [e - b for b, e in edges]
+            assert max(sizes) - min(sizes) <= 4 + 3
+    with pytest.raises(capi.MppiError):
+        capi.shard_range(10, 3, 2)
+
+
+def test_invalid_parameters_are_rejected():
+    lib = capi.load()
+    p = capi.MppiParams()
+    lib.mppi_params_default(C.byref(p))
+    h = C.c_void_p()
+    p.samples, p.horizon, p.dt, p.act_dim, p.state_dim = 100, 10, 0.1, 2, 5
+    assert lib.mppi_create(C.byref(p), C.byref(h)) == capi.ERR_INVALID
+    assert b"state_dim" in lib.mppi_last_error()
+    p.state_dim, p.act_dim = 10, 5
+    assert lib.mppi_create(C.byref(p), C.byref(h)) == capi.ERR_INVALID
+    p.state_dim, p.act_dim, p.struct_size = 4, 2, 12
+    assert lib.mppi_create(C.byref(p), C.byref(h)) == capi.ERR_INVALID
+    assert b"ABI" in lib.mppi_last_error()
+
+
+def test_no_silent_cpu_fallback():
+    """Without a CUDA device mppi_create must fail with MPPI_ERR_NO_DEVICE."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = capi.load()
+    p = capi.MppiParams()
+    lib.mppi_params_default(C.byref(p))
+    p.samples, p.horizon, p.dt, p.act_dim, p.state_dim = 100, 10, 0.1, 2, 4
+    h = C.c_void_p()
+    assert lib.mppi_create(C.byref(p), C.byref(h)) == capi.ERR_NO_DEVICE
+    assert not h.value
+    assert b"no CPU fallback" in lib.mppi_last_error()
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under mppi_gpu_b200/, include/ or cpp/ may reference oracle/."""
+    bad = []
+    for top in ("mppi_gpu_b200", "include", "cpp"):
+        for dp, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", "Makefile")):
+                    txt = open(os.path.join(dp, f), errors="replace").read()
+                    if re.search(r"(import|from)\s+oracle|oracle/|liboracle|pyoracle", txt):
+                        # comments that merely name the oracle's restatement are fine
+                        hits = [l for l in txt.splitlines()
+                                if re.search(r"(import|from)\s+oracle|liboracle|pyoracle|#include.*oracle", l)]
+                        if hits:
+                            bad.append((os.path.join(dp, f), hits))
+    assert not bad, bad
