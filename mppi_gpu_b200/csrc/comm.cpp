@@ -94,11 +94,11 @@ bool NcclComm::allreduce_min_u64(unsigned long long *buf, size_t count, cudaStre
                  "ncclAllReduce(min,u64)", err);
 }
 
-bool NcclComm::allreduce_sum_f32(float *buf, size_t count, cudaStream_t s, std::string &err)
+bool NcclComm::allreduce_sum_i64(long long *buf, size_t count, cudaStream_t s, std::string &err)
 {
-    return check(api().AllReduce(buf, buf, count, ncclFloat32, ncclSum,
+    return check(api().AllReduce(buf, buf, count, ncclInt64, ncclSum,
                                  static_cast<ncclComm_t>(comm_), s),
-                 "ncclAllReduce(sum,f32)", err);
+                 "ncclAllReduce(sum,i64)", err);
 }
 
 }  // namespace mppi

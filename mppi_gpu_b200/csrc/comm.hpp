@@ -23,8 +23,8 @@ public:
     bool init(int rank, int world, const uint8_t *id128, std::string &err);
     // in-place all-reduce(min) of `count` uint64 values
     bool allreduce_min_u64(unsigned long long *buf, size_t count, cudaStream_t s, std::string &err);
-    // in-place all-reduce(sum) of `count` floats
-    bool allreduce_sum_f32(float *buf, size_t count, cudaStream_t s, std::string &err);
+    // in-place all-reduce(sum) of `count` int64 fixed-point accumulators (exact)
+    bool allreduce_sum_i64(long long *buf, size_t count, cudaStream_t s, std::string &err);
     bool ready() const { return comm_ != nullptr; }
 
 private:

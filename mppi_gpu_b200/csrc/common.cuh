@@ -38,7 +38,7 @@ struct CtlDev {
     unsigned long long step;      // control-step counter == Philox counter words 2,3
     unsigned long long last_key;  // min_key of the last finished step (for get_step_info)
     float eta;                    // normaliser of the last finished step
-    float eta_local;              // this shard's part of it
+    float pad_;
 };
 
 constexpr unsigned long long kMinKeyInit = ~0ull;
@@ -81,6 +81,24 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
         v = t < v ? t : v;
     }
     return v;
+}
+
+// ---------------------------------------------------------------------------------
+// Cross-CTA / cross-GPU sums are taken in 64-bit fixed point (scale 2^30, range +-8.6e9,
+// resolution 9.3e-10): integer addition is associative, so atomics and all-reduces give
+// the same bits whatever the arrival order.  Each contribution is a float partial that is
+// already the sum of >= 256 terms; its conversion error (<= 4.7e-10) is far below the
+// float32 rounding of the result.
+// ---------------------------------------------------------------------------------
+constexpr double kAccScale = 1073741824.0;           // 2^30
+__device__ __forceinline__ void acc_add(long long *acc, float v)
+{
+    const long long q = __double2ll_rn((double)v * kAccScale);
+    atomicAdd(reinterpret_cast<unsigned long long *>(acc), (unsigned long long)q);
+}
+__device__ __forceinline__ float acc_to_float(long long q)
+{
+    return (float)((double)q * (1.0 / kAccScale));
 }
 
 // ---------------------------------------------------------------------------------

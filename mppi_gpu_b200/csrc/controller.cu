@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -54,9 +55,9 @@ struct mppi_handle {
     LaunchCtx ctx{};
     int R = 0, S = 0;
 
-    float *d_eps = nullptr, *d_S = nullptr, *d_wt = nullptr, *d_partials = nullptr;
-    float *d_eta_part = nullptr, *d_red = nullptr, *d_U = nullptr, *d_Uprev = nullptr;
-    float *d_next = nullptr;
+    float *d_eps = nullptr, *d_S = nullptr, *d_wt = nullptr;
+    long long *d_acc = nullptr;   // [R+1] fixed-point accumulators (rows, eta)
+    float *d_U = nullptr, *d_Uprev = nullptr, *d_next = nullptr;
     ProblemDev *d_prob = nullptr;
     CtlDev *d_ctl = nullptr;
 
@@ -120,7 +121,7 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
         return evs ? cudaEventRecord(evs[ei++], c.stream) : cudaSuccess;
     };
     CK(mark());
-    if (sample && !fused(h)) CK(launch_sample(c, h->d_eps, h->d_prob, h->d_ctl, false, 0));
+    if (sample && !fused(h)) CK(launch_sample(c, h->d_eps, h->d_ctl, false, 0));
     CK(mark());
     CK(launch_rollout(c, h->d_eps, h->d_U, h->d_prob, h->d_S, h->d_ctl, sample && fused(h)));
     CK(mark());
@@ -129,23 +130,17 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
             return fail(MPPI_ERR_COMM, "%s", err.c_str());
     }
     CK(mark());
-    CK(launch_weights(c, h->d_S, h->d_prob, h->d_ctl, h->d_wt, h->d_eta_part));
+    CK(launch_weights(c, h->d_S, h->d_prob, h->d_ctl, h->d_wt, h->d_acc));
     CK(mark());
-    CK(launch_average(c, h->tmap, h->d_wt, h->d_partials));
+    CK(launch_average(c, h->tmap, h->d_wt, h->d_acc));
     CK(mark());
     if (multi(h)) {
-        CK(launch_finalize(c, true, false, h->d_partials, h->d_eta_part, h->d_red, h->d_U,
-                           h->d_Uprev, h->d_prob, h->d_ctl, h->d_next, h->p.flags));
-        if (!h->comm.allreduce_sum_f32(h->d_red, (size_t)h->R + 1, c.stream, err))
+        if (!h->comm.allreduce_sum_i64(h->d_acc, (size_t)h->R + 1, c.stream, err))
             return fail(MPPI_ERR_COMM, "%s", err.c_str());
-        CK(mark());
-        CK(launch_finalize(c, false, true, h->d_partials, h->d_eta_part, h->d_red, h->d_U,
-                           h->d_Uprev, h->d_prob, h->d_ctl, h->d_next, h->p.flags));
-    } else {
-        CK(mark());
-        CK(launch_finalize(c, true, true, h->d_partials, h->d_eta_part, h->d_red, h->d_U,
-                           h->d_Uprev, h->d_prob, h->d_ctl, h->d_next, h->p.flags));
     }
+    CK(mark());
+    CK(launch_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
+                       h->p.flags));
     CK(cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * h->p.act_dim, cudaMemcpyDeviceToHost,
                        c.stream));
     CK(mark());
@@ -156,7 +151,6 @@ int kernels_per_step(const mppi_handle *h, bool sample)
 {
     int n = 4;                                  // rollout, weights, average, finalize
     if (sample && !fused(h)) n += 1;            // sampling
-    if (multi(h)) n += 1;                       // finalize split in fold + update
     return n;
 }
 
@@ -239,8 +233,8 @@ int mppi_destroy(mppi_handle *h)
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
-    cudaFree(h->d_eps); cudaFree(h->d_S); cudaFree(h->d_wt); cudaFree(h->d_partials);
-    cudaFree(h->d_eta_part); cudaFree(h->d_red); cudaFree(h->d_U); cudaFree(h->d_Uprev);
+    cudaFree(h->d_eps); cudaFree(h->d_S); cudaFree(h->d_wt); cudaFree(h->d_acc);
+    cudaFree(h->d_U); cudaFree(h->d_Uprev);
     cudaFree(h->d_next); cudaFree(h->d_prob); cudaFree(h->d_ctl);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_next) cudaFreeHost(h->h_next);
@@ -310,8 +304,17 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     c.num_sms = prop.multiProcessorCount;
     const long long ntiles = (c.k_pad / kAvgTileK) * (long long)((h->R + kAvgTileR - 1) / kAvgTileR);
     c.avg_grid = (int)(ntiles < c.num_sms ? ntiles : c.num_sms);
-    c.avg_gpad = (c.avg_grid + 31) / 32 * 32;
     c.weights_blocks = (int)((c.k_pad + kWeightsBlockSamples - 1) / kWeightsBlockSamples);
+    c.sampler = make_sampler_params(p.seed, p.sigma, p.act_dim);
+    // samples per rollout thread: wide vectors once there are enough samples for many waves
+    {
+        const double waves4 = (double)c.k_pad / 4.0 / (512.0 * c.num_sms);
+        c.rollout_spt = waves4 >= 8.0 ? 4 : (waves4 >= 2.0 ? 2 : 1);
+        if (const char *env = getenv("MPPI_ROLLOUT_SPT")) {
+            const int v = atoi(env);
+            if (v == 1 || v == 2 || v == 4) c.rollout_spt = v;
+        }
+    }
 
     int rc = MPPI_OK;
 #define CKH(call)                                                                         \
@@ -331,9 +334,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     CKH(cudaMalloc(&h->d_eps, eps_bytes));
     CKH(cudaMalloc(&h->d_S, sizeof(float) * (size_t)c.k_pad));
     CKH(cudaMalloc(&h->d_wt, sizeof(float) * (size_t)c.k_pad));
-    CKH(cudaMalloc(&h->d_partials, sizeof(float) * (size_t)h->R * c.avg_gpad));
-    CKH(cudaMalloc(&h->d_eta_part, sizeof(float) * (size_t)c.weights_blocks));
-    CKH(cudaMalloc(&h->d_red, sizeof(float) * ((size_t)h->R + 1)));
+    CKH(cudaMalloc(&h->d_acc, sizeof(long long) * ((size_t)h->R + 1)));
     CKH(cudaMalloc(&h->d_U, sizeof(float) * (size_t)h->R));
     CKH(cudaMalloc(&h->d_Uprev, sizeof(float) * (size_t)h->R));
     CKH(cudaMalloc(&h->d_next, sizeof(float) * kMaxAct));
@@ -346,10 +347,9 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     CKH(cudaMemsetAsync(h->d_eps, 0, eps_bytes, h->stream));
     CKH(cudaMemsetAsync(h->d_S, 0, sizeof(float) * (size_t)c.k_pad, h->stream));
     CKH(cudaMemsetAsync(h->d_wt, 0, sizeof(float) * (size_t)c.k_pad, h->stream));
-    CKH(cudaMemsetAsync(h->d_partials, 0, sizeof(float) * (size_t)h->R * c.avg_gpad, h->stream));
+    CKH(cudaMemsetAsync(h->d_acc, 0, sizeof(long long) * ((size_t)h->R + 1), h->stream));
     CKH(cudaMemsetAsync(h->d_U, 0, sizeof(float) * (size_t)h->R, h->stream));
     CKH(cudaMemsetAsync(h->d_Uprev, 0, sizeof(float) * (size_t)h->R, h->stream));
-    CKH(cudaMemsetAsync(h->d_red, 0, sizeof(float) * ((size_t)h->R + 1), h->stream));
     CKH(launch_clear_ctl(c, h->d_ctl));
     for (auto &e : h->ev) CKH(cudaEventCreate(&e));
     CKH(cudaEventCreate(&h->t0));
@@ -470,7 +470,7 @@ int mppi_step_enqueue(mppi_handle *h)
         if (h->profiling) {
             CK(cudaStreamSynchronize(h->stream));
             // event i+1 closes stage i of {sample, rollout, comm_min, weights, average,
-            // (fold+)comm_sum, finalize(+D2H)}
+            // comm_sum, finalize(+D2H)}
             for (int i = 0; i < MPPI_K_COUNT; ++i) {
                 float ms = 0.f;
                 CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
@@ -618,7 +618,7 @@ int mppi_sample_only(mppi_handle *h, uint64_t step)
 {
     int rc = check_handle(h);
     if (rc) return rc;
-    CK(launch_sample(h->ctx, h->d_eps, h->d_prob, h->d_ctl, true, step));
+    CK(launch_sample(h->ctx, h->d_eps, h->d_ctl, true, step));
     CK(cudaStreamSynchronize(h->stream));
     h->total_launches += 1;
     return MPPI_OK;

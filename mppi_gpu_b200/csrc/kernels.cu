@@ -6,7 +6,7 @@
 //                                    (The reference keeps [K][T][A], src/point_mass.cu:784,
 //                                    which makes every per-sample access a T*A-float stride.)
 //   S, wt    [k_pad]                 rollout costs and unnormalised weights
-//   partials [R][gpad]               per-CTA partial sums of the weighted average
+//   acc      [R+1] int64             fixed-point (2^-30) accumulators: sum_k wt_k eps[r][k], eta
 //   U, U_prev[T*A]
 //
 // Kernel chain of a control step (reference: PointMassModel::get_act, src/point_mass.cu:129-203):
@@ -19,34 +19,32 @@ namespace mppi {
 // =================================================================================
 // (1) sampling: replaces curand_normal in PointMassModelGpu::step
 //     (src/point_mass_gpu.cu:85-90).  HBM-write bound: 4*K*T*A bytes.
+//     One thread owns a quad of samples (one float4 column of eps) and a block of
+//     consecutive time steps; per (t,a) one Philox call -> one 16-byte store, 512 B per
+//     warp and row.  No per-row branches: the action index is the unrolled inner loop.
 // =================================================================================
-constexpr int kSampleRowsPerThread = 4;
-
 template <int A>
 __global__ void __launch_bounds__(256)
-sample_kernel(float *__restrict__ eps, size_t ld, int rows, const ProblemDev *__restrict__ prob,
-              const CtlDev *__restrict__ ctl, unsigned long long k_offset, unsigned long long seed,
-              int use_step_override, unsigned long long step_override)
+sample_kernel(float *__restrict__ eps, size_t ld, int T, int t_per_cta,
+              const CtlDev *__restrict__ ctl, unsigned long long k_offset,
+              const __grid_constant__ SamplerParams sp, int use_step_override,
+              unsigned long long step_override)
 {
     const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // local quad
     if (4 * q >= ld) return;
     const unsigned long long step = use_step_override ? step_override : ctl->step;
     const uint32_t qg = (uint32_t)((k_offset >> 2) + q);                 // global quad
-    float sig[A];
+    const int t0 = blockIdx.y * t_per_cta;
+    const int t1 = min(T, t0 + t_per_cta);
+    float *p = eps + (size_t)t0 * A * ld + 4 * q;
+    uint32_t r = (uint32_t)(t0 * A);
+#pragma unroll 2
+    for (int t = t0; t < t1; ++t) {
 #pragma unroll
-    for (int a = 0; a < A; ++a) sig[a] = prob->sigma[a];
-
-    const int r0 = blockIdx.y * kSampleRowsPerThread;
-#pragma unroll
-    for (int j = 0; j < kSampleRowsPerThread; ++j) {
-        const int r = r0 + j;
-        if (r < rows) {
-            float4 n = normal4(qg, (uint32_t)r, step, seed);
-            float s = sig[0];
-#pragma unroll
-            for (int a = 1; a < A; ++a) s = (r % A == a) ? sig[a] : s;
-            n.x *= s; n.y *= s; n.z *= s; n.w *= s;
-            stg_f4(eps + (size_t)r * ld + 4 * q, n);
+        for (int a = 0; a < A; ++a) {
+            stg_f4(p, sample4(qg, r, step, sp, sp.c[a]));
+            p += ld;
+            ++r;
         }
     }
 }
@@ -114,90 +112,173 @@ struct PointMass {
     }
 };
 
-template <int A, bool STRICT, bool FUSED>
-__global__ void __launch_bounds__(256)
+// vector load of SPT consecutive floats through the non-coherent, no-L1-allocate path
+template <int SPT> struct EpsVec;
+template <> struct EpsVec<1> {
+    static __device__ __forceinline__ void load(const float *p, float (&v)[1])
+    {
+        asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v[0]) : "l"(p));
+    }
+};
+template <> struct EpsVec<2> {
+    static __device__ __forceinline__ void load(const float *p, float (&v)[2])
+    {
+        asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
+    }
+};
+template <> struct EpsVec<4> {
+    static __device__ __forceinline__ void load(const float *p, float (&v)[4])
+    {
+        asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+            : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+    }
+};
+
+// U staging in shared memory: per time step one 16-byte aligned record
+// {u_0, u_0*inv_s_0, u_1, u_1*inv_s_1, ...} so a thread fetches a whole step with one or two
+// LDS.128 (broadcast) instead of 2A scalar loads.
+template <int A> struct UStage {
+    static constexpr int kStride = (2 * A + 3) / 4 * 4;     // floats per step
+    static __device__ __forceinline__ void fetch(const float *s, int t, float (&u)[A], float (&ui)[A])
+    {
+        const float4 *p = reinterpret_cast<const float4 *>(s + (size_t)t * kStride);
+        const float4 v0 = p[0];
+        u[0] = v0.x; ui[0] = v0.y;
+        if (A >= 2) { u[1 % A] = v0.z; ui[1 % A] = v0.w; }
+        if (A >= 3) {
+            const float4 v1 = p[1];
+            u[2 % A] = v1.x; ui[2 % A] = v1.y;
+            if (A >= 4) { u[3 % A] = v1.z; ui[3 % A] = v1.w; }
+        }
+    }
+};
+
+// One thread integrates SPT consecutive samples.  eps is consumed in chunks of CH time
+// steps through a register double buffer: the loads of chunk c+1 are issued before the
+// arithmetic of chunk c, so every thread keeps CH*A vector loads (96 B for A=3) in flight.
+template <int A, bool STRICT, bool FUSED, int SPT>
+__global__ void __launch_bounds__(256, (SPT == 1 ? 3 : 2))
 rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
                const float *__restrict__ U, const ProblemDev *__restrict__ prob,
                float *__restrict__ S, CtlDev *__restrict__ ctl, unsigned long long k_offset,
-               unsigned long long seed)
+               const __grid_constant__ SamplerParams sp)
 {
-    extern __shared__ float smem_f[];
-    float *sU  = smem_f;            // U[t][a]
-    float *sUi = smem_f + T * A;    // U[t][a] * inv_s[a]   (src/cost.cu:46)
+    static_assert(!FUSED || SPT == 4, "fused sampling works on Philox quads");
+    constexpr int CH = 8 / SPT;
+    constexpr int UST = UStage<A>::kStride;
+    extern __shared__ __align__(16) float smem_f[];          // [T][UST]
     __shared__ unsigned long long s_key[8];
 
     for (int i = threadIdx.x; i < T * A; i += blockDim.x) {
         const float u = U[i];
-        sU[i]  = u;
-        sUi[i] = __fmul_rn(u, prob->inv_s[i % A]);
+        const int t = i / A, a = i - t * A;
+        smem_f[t * UST + 2 * a]     = u;
+        smem_f[t * UST + 2 * a + 1] = __fmul_rn(u, prob->inv_s[a]);   // src/cost.cu:46
     }
     __syncthreads();
 
-    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // group of SPT samples
     unsigned long long key = kMinKeyInit;
 
-    if (4 * q < ld) {
+    if (SPT * g < ld) {
         PointMass<A, STRICT> m;
         m.load(prob);
-        float x[4][2 * A];
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        float x[SPT][2 * A];
+        float c[SPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < SPT; ++j) {
+            c[j] = 0.0f;
 #pragma unroll
             for (int i = 0; i < 2 * A; ++i) x[j][i] = prob->x0[i];
-
-        float sig[A];
-        unsigned long long step = 0;
-        uint32_t qg = 0;
-        if (FUSED) {
-#pragma unroll
-            for (int a = 0; a < A; ++a) sig[a] = prob->sigma[a];
-            step = ctl->step;
-            qg = (uint32_t)((k_offset >> 2) + q);
         }
+        float *ep = eps + SPT * g;
 
-        float *ep = eps + 4 * q;
-#pragma unroll 4
-        for (int t = 0; t < T; ++t) {
-            float4 e4[A];
+        // one time step for all SPT samples given the eps vectors e[a][j]
+        auto advance = [&](int t, const float (&e)[A][SPT]) {
             float u[A], ui[A];
+            UStage<A>::fetch(smem_f, t, u, ui);
 #pragma unroll
-            for (int a = 0; a < A; ++a) {
-                const int r = t * A + a;
-                if (FUSED) {
-                    float4 n = normal4(qg, (uint32_t)r, step, seed);
-                    n.x *= sig[a]; n.y *= sig[a]; n.z *= sig[a]; n.w *= sig[a];
-                    stg_f4(ep + (size_t)r * ld, n);
-                    e4[a] = n;
-                } else {
-                    e4[a] = ldg_stream_f4(ep + (size_t)r * ld);
-                }
-                u[a]  = sU[r];
-                ui[a] = sUi[r];
+            for (int j = 0; j < SPT; ++j) {
+                float ej[A];
+#pragma unroll
+                for (int a = 0; a < A; ++a) ej[a] = e[a][j];
+                m.step(x[j], c[j], u, ui, ej);
             }
-            float e[A];
+        };
+
+        if (FUSED) {
+            const unsigned long long step = ctl->step;
+            const uint32_t qg = (uint32_t)((k_offset >> 2) + g);
+            uint32_t r = 0;
+            float *pw = ep;
+#pragma unroll 2
+            for (int t = 0; t < T; ++t) {
+                float e[A][SPT];
 #pragma unroll
-            for (int a = 0; a < A; ++a) e[a] = e4[a].x;
-            m.step(x[0], c[0], u, ui, e);
+                for (int a = 0; a < A; ++a) {
+                    const float4 n = sample4(qg, r, step, sp, sp.c[a]);
+                    stg_f4(pw, n);
+                    pw += ld;
+                    e[a][0] = n.x; e[a][1 % SPT] = n.y; e[a][2 % SPT] = n.z; e[a][3 % SPT] = n.w;
+                    ++r;
+                }
+                advance(t, e);
+            }
+        } else {
+            float bufA[CH][A][SPT], bufB[CH][A][SPT];
+            const float *pl = ep;                      // next chunk to load
+            auto load_full = [&](float (&buf)[CH][A][SPT]) {
 #pragma unroll
-            for (int a = 0; a < A; ++a) e[a] = e4[a].y;
-            m.step(x[1], c[1], u, ui, e);
+                for (int i = 0; i < CH; ++i)
 #pragma unroll
-            for (int a = 0; a < A; ++a) e[a] = e4[a].z;
-            m.step(x[2], c[2], u, ui, e);
+                    for (int a = 0; a < A; ++a)
+                        EpsVec<SPT>::load(pl + (size_t)(i * A + a) * ld, buf[i][a]);
+                pl += (size_t)(CH * A) * ld;
+            };
+            auto load_guard = [&](float (&buf)[CH][A][SPT], int t0) {
 #pragma unroll
-            for (int a = 0; a < A; ++a) e[a] = e4[a].w;
-            m.step(x[3], c[3], u, ui, e);
+                for (int i = 0; i < CH; ++i)
+                    if (t0 + i < T) {
+#pragma unroll
+                        for (int a = 0; a < A; ++a)
+                            EpsVec<SPT>::load(pl + (size_t)(i * A + a) * ld, buf[i][a]);
+                    }
+                pl += (size_t)(CH * A) * ld;
+            };
+            auto run_full = [&](const float (&buf)[CH][A][SPT], int t0) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) advance(t0 + i, buf[i]);
+            };
+            auto run_guard = [&](const float (&buf)[CH][A][SPT], int t0) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i)
+                    if (t0 + i < T) advance(t0 + i, buf[i]);
+            };
+            int t0 = 0;
+            load_guard(bufA, 0);
+            // steady state: chunks t0 (in bufA), t0+CH and t0+2CH are complete
+#pragma unroll 1
+            for (; t0 + 3 * CH <= T; t0 += 2 * CH) {
+                load_full(bufB);
+                run_full(bufA, t0);
+                load_full(bufA);
+                run_full(bufB, t0 + CH);
+            }
+#pragma unroll 1
+            for (; t0 < T; t0 += 2 * CH) {
+                load_guard(bufB, t0 + CH);
+                run_guard(bufA, t0);
+                load_guard(bufA, t0 + 2 * CH);
+                run_guard(bufB, t0 + CH);
+            }
         }
         // terminal cost on x[T] (charged on top of the last stage cost,
         // src/point_mass_gpu.cu:116)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) c[j] = __fadd_rn(c[j], m.state_cost(x[j], 0.0f));
-
-        stg_f4(S + 4 * q, make_float4(c[0], c[1], c[2], c[3]));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const long long k = (long long)(4 * q) + j;
+        for (int j = 0; j < SPT; ++j) {
+            c[j] = __fadd_rn(c[j], m.state_cost(x[j], 0.0f));
+            S[SPT * g + j] = c[j];
+            const long long k = (long long)(SPT * g) + j;
             if (k < k_local) {
                 const unsigned long long kk =
                     ((unsigned long long)float_to_ordered(c[j]) << 32) |
@@ -219,12 +300,13 @@ rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
 
 // =================================================================================
 // (3) weights: exp_red + sum_red (src/point_mass.cu:510-531, :628-666) in one pass.
-//     wt[k] = expf(-(1/lambda) * (S[k] - beta)); deterministic per-CTA eta partial.
+//     wt[k] = expf(-(1/lambda) * (S[k] - beta)); the CTA's eta partial is added to the
+//     fixed-point accumulator acc[R] (integer atomics: exact, order independent).
 // =================================================================================
 __global__ void __launch_bounds__(256)
 weights_kernel(const float *__restrict__ S, long long k_local, long long k_pad,
                const ProblemDev *__restrict__ prob, const CtlDev *__restrict__ ctl,
-               float *__restrict__ wt, float *__restrict__ eta_part)
+               float *__restrict__ wt, long long *__restrict__ acc_eta)
 {
     __shared__ float s_sum[8];
     const float beta = ordered_to_float((uint32_t)(ctl->min_key >> 32));
@@ -247,7 +329,7 @@ weights_kernel(const float *__restrict__ S, long long k_local, long long k_pad,
     if (threadIdx.x < 32) {
         s = threadIdx.x < 8 ? s_sum[threadIdx.x] : 0.0f;
         s = warp_sum(s);
-        if (threadIdx.x == 0) eta_part[blockIdx.x] = s;
+        if (threadIdx.x == 0 && s != 0.0f) acc_add(acc_eta, s);
     }
 }
 
@@ -263,9 +345,11 @@ weights_kernel(const float *__restrict__ S, long long k_local, long long k_pad,
 //     weights, landing on an mbarrier; kAvgStages tiles are in flight per SM.  Warps 0-7
 //     consume: warp w owns the rows {w, w+8, ...} of every tile, each lane multiplies its 8
 //     samples of the row by the weights held in registers, the warp shuffle-reduces and lane 0
-//     accumulates the row sum in shared memory.  The tile -> CTA assignment is static, every
-//     row sum is formed in a fixed order, the per-CTA partials are written once at the end:
-//     bitwise reproducible.
+//     accumulates the row sum in shared memory.  The tile -> CTA assignment is static and
+//     every CTA's row sum is formed in a fixed order; the cross-CTA sum is taken in 64-bit
+//     fixed point with integer atomics (acc[r] += round(partial * 2^30)), which is exact and
+//     order independent: the result is bitwise reproducible run to run, and the same
+//     accumulators are what a multi-GPU run all-reduces.
 // =================================================================================
 size_t average_smem_bytes(int R)
 {
@@ -278,7 +362,7 @@ size_t average_smem_bytes(int R)
 
 __global__ void __launch_bounds__(kAvgThreads, 1)
 average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__restrict__ wt,
-               float *__restrict__ partials, int gpad, int rows, int nslab, int nchunk)
+               long long *__restrict__ acc, int rows, int nslab, int nchunk)
 {
     extern __shared__ uint8_t smem_raw[];
     // 128-byte aligned carve-up (TMA destinations need 128 B)
@@ -375,86 +459,54 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
         }
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < rows; r += blockDim.x)
-        partials[(size_t)r * gpad + blockIdx.x] = s_row[r];
+    if (t_end > t_begin)
+        for (int r = threadIdx.x; r < rows; r += blockDim.x) acc_add(acc + r, s_row[r]);
 }
 
 // =================================================================================
-// (5) finalize: fold the per-CTA partials and eta (replaces sum_red_adim,
-//     src/point_mass.cu:668-741), U += num/eta (copy_act, :756-761), next action = U[0,:]
-//     (:195), receding-horizon shift with repeat-last / init-act re-initialisation
-//     (shift_act, :805-824), step counter advance and min_key re-arm.  One CTA.
-//     Multi-shard: FOLD writes red[0..R-1] = num, red[R] = eta_local for the all-reduce;
-//     UPDATE consumes the reduced vector.
+// (5) finalize: U += num/eta (copy_act, src/point_mass.cu:756-761) from the fixed-point
+//     accumulators acc[0..R-1] = sum_k w~_k eps_k[r], acc[R] = eta (replaces the per-t
+//     sum_red_adim folds, :668-741), next action = U[0,:] (:195), receding-horizon shift with
+//     repeat-last / init-act re-initialisation (shift_act, :805-824), step counter advance,
+//     accumulators and min key re-armed for the next step.  One small CTA.
+//     Multi-shard: acc has been all-reduced (int64 sum, exact) before this kernel.
 // =================================================================================
-constexpr int kFinThreads = 1024;
+constexpr int kFinThreads = 256;
 
-template <bool FOLD, bool UPDATE>
 __global__ void __launch_bounds__(kFinThreads)
-finalize_kernel(const float *__restrict__ partials, int gpad, int ncta,
-                const float *__restrict__ eta_part, int neta, float *__restrict__ red,
-                float *__restrict__ U, float *__restrict__ U_prev,
+finalize_kernel(long long *__restrict__ acc, float *__restrict__ U, float *__restrict__ U_prev,
                 const ProblemDev *__restrict__ prob, CtlDev *__restrict__ ctl,
                 float *__restrict__ next_act, int T, int A, unsigned flags)
 {
     extern __shared__ float s_u[];          // U_new [T*A]
-    __shared__ float s_red[32];
-    __shared__ float s_eta;
     const int R = T * A;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (FOLD) {
-        // eta: strided per-thread serial sums, then a fixed-shape tree
-        float e = 0.0f;
-        for (int i = threadIdx.x; i < neta; i += kFinThreads) e += eta_part[i];
-        e = warp_sum(e);
-        if (lane == 0) s_red[warp] = e;
-        __syncthreads();
-        if (warp == 0) {
-            e = s_red[lane];
-            e = warp_sum(e);
-            if (lane == 0) { s_eta = e; red[R] = e; }
+    const float eta = acc_to_float(acc[R]);
+    for (int i = threadIdx.x; i < R; i += kFinThreads) {
+        const float u = U[i];
+        float un = u + acc_to_float(acc[i]) / eta;
+        if (flags & MPPI_FLAG_CLAMP_ACTIONS) {
+            const float m = prob->max_act[i % A];
+            un = fminf(fmaxf(un, -m), m);
         }
-        // rows: one warp per row, lanes stride over the CTA partials
-        for (int r = warp; r < R; r += kFinThreads / 32) {
-            const float *p = partials + (size_t)r * gpad;
-            float s = 0.0f;
-            for (int g = lane; g < ncta; g += 32) s += p[g];
-            s = warp_sum(s);
-            if (lane == 0) red[r] = s;
-        }
-        __syncthreads();
+        U_prev[i] = u;
+        s_u[i] = un;
     }
-    if (UPDATE) {
-        const float eta = FOLD ? s_eta : red[R];
-        for (int i = threadIdx.x; i < R; i += kFinThreads) {
-            const float u = U[i];
-            float un = u + red[i] / eta;
-            if (flags & MPPI_FLAG_CLAMP_ACTIONS) {
-                const float m = prob->max_act[i % A];
-                un = fminf(fmaxf(un, -m), m);
-            }
-            U_prev[i] = u;
-            s_u[i] = un;
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < R; i += kFinThreads) {
-            float v;
-            if (i < R - A)                              v = s_u[i + A];
-            else if (flags & MPPI_FLAG_REINIT_INIT_ACT) v = prob->init_act[i - (R - A)];
-            else                                        v = s_u[i];
-            U[i] = v;
-        }
-        if (threadIdx.x < A) next_act[threadIdx.x] = s_u[threadIdx.x];
-        if (threadIdx.x == 0) {
-            ctl->eta = eta;
-            ctl->eta_local = FOLD ? s_eta : ctl->eta_local;
-            ctl->last_key = ctl->min_key;
-            ctl->min_key = kMinKeyInit;
-            ctl->step = ctl->step + 1;
-        }
-    } else if (FOLD) {
-        if (threadIdx.x == 0) ctl->eta_local = s_eta;
+    __syncthreads();
+    for (int i = threadIdx.x; i < R; i += kFinThreads) {
+        float v;
+        if (i < R - A)                              v = s_u[i + A];
+        else if (flags & MPPI_FLAG_REINIT_INIT_ACT) v = prob->init_act[i - (R - A)];
+        else                                        v = s_u[i];
+        U[i] = v;
+        acc[i] = 0;
+    }
+    if (threadIdx.x < A) next_act[threadIdx.x] = s_u[threadIdx.x];
+    if (threadIdx.x == 0) {
+        acc[R] = 0;
+        ctl->eta = eta;
+        ctl->last_key = ctl->min_key;
+        ctl->min_key = kMinKeyInit;
+        ctl->step = ctl->step + 1;
     }
 }
 
@@ -556,7 +608,6 @@ __global__ void clear_ctl_kernel(CtlDev *ctl)
     ctl->last_key = kMinKeyInit;
     ctl->step = 0;
     ctl->eta = 0.0f;
-    ctl->eta_local = 0.0f;
 }
 
 // =================================================================================
@@ -571,82 +622,82 @@ __global__ void clear_ctl_kernel(CtlDev *ctl)
         default: return cudaErrorInvalidValue;                          \
     }
 
-cudaError_t launch_sample(const LaunchCtx &c, float *eps, const ProblemDev *prob, const CtlDev *ctl,
+cudaError_t launch_sample(const LaunchCtx &c, float *eps, const CtlDev *ctl,
                           bool use_step_override, unsigned long long step_override)
 {
     const size_t quads = (size_t)c.k_pad / 4;
-    dim3 grid((unsigned)((quads + 255) / 256),
-              (unsigned)((c.rows + kSampleRowsPerThread - 1) / kSampleRowsPerThread));
+    const unsigned gx = (unsigned)((quads + 255) / 256);
+    // enough CTAs for >= ~8 per SM, at most 16 time steps per thread
+    int tpc = (int)(((long long)c.horizon * gx) / (8ll * c.num_sms));
+    tpc = tpc < 1 ? 1 : (tpc > 16 ? 16 : tpc);
+    dim3 grid(gx, (unsigned)((c.horizon + tpc - 1) / tpc));
     MPPI_DISPATCH_A(c.act_dim,
-        sample_kernel<kA><<<grid, 256, 0, c.stream>>>(eps, (size_t)c.k_pad, c.rows, prob, ctl,
-                                                      (unsigned long long)c.k_offset, c.seed,
+        sample_kernel<kA><<<grid, 256, 0, c.stream>>>(eps, (size_t)c.k_pad, c.horizon, tpc, ctl,
+                                                      (unsigned long long)c.k_offset, c.sampler,
                                                       use_step_override ? 1 : 0, step_override));
     return cudaGetLastError();
 }
 
-template <int A, bool STRICT, bool FUSED>
+template <int A, bool STRICT, bool FUSED, int SPT>
 static cudaError_t launch_rollout_t(const LaunchCtx &c, float *eps, const float *U,
                                     const ProblemDev *prob, float *S, CtlDev *ctl)
 {
-    const size_t quads = (size_t)c.k_pad / 4;
-    const unsigned grid = (unsigned)((quads + 255) / 256);
-    const size_t smem = 2 * sizeof(float) * (size_t)c.rows;
-    auto kern = rollout_kernel<A, STRICT, FUSED>;
-    kern<<<grid, 256, smem, c.stream>>>(eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U,
-                                        prob, S, ctl, (unsigned long long)c.k_offset, c.seed);
+    const size_t groups = (size_t)c.k_pad / SPT;
+    const unsigned grid = (unsigned)((groups + 255) / 256);
+    const size_t smem = sizeof(float) * (size_t)c.horizon * UStage<A>::kStride;
+    rollout_kernel<A, STRICT, FUSED, SPT><<<grid, 256, smem, c.stream>>>(
+        eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U, prob, S, ctl,
+        (unsigned long long)c.k_offset, c.sampler);
     return cudaGetLastError();
+}
+
+template <int A, bool STRICT>
+static cudaError_t launch_rollout_a(const LaunchCtx &c, float *eps, const float *U,
+                                    const ProblemDev *prob, float *S, CtlDev *ctl, bool fused)
+{
+    if (fused) return launch_rollout_t<A, STRICT, true, 4>(c, eps, U, prob, S, ctl);
+    switch (c.rollout_spt) {
+        case 1: return launch_rollout_t<A, STRICT, false, 1>(c, eps, U, prob, S, ctl);
+        case 2: return launch_rollout_t<A, STRICT, false, 2>(c, eps, U, prob, S, ctl);
+        default: return launch_rollout_t<A, STRICT, false, 4>(c, eps, U, prob, S, ctl);
+    }
 }
 
 cudaError_t launch_rollout(const LaunchCtx &c, float *eps, const float *U, const ProblemDev *prob,
                            float *S, CtlDev *ctl, bool fused)
 {
     MPPI_DISPATCH_A(c.act_dim,
-        if (c.strict) {
-            return fused ? launch_rollout_t<kA, true, true>(c, eps, U, prob, S, ctl)
-                         : launch_rollout_t<kA, true, false>(c, eps, U, prob, S, ctl);
-        } else {
-            return fused ? launch_rollout_t<kA, false, true>(c, eps, U, prob, S, ctl)
-                         : launch_rollout_t<kA, false, false>(c, eps, U, prob, S, ctl);
-        });
+        return c.strict ? launch_rollout_a<kA, true>(c, eps, U, prob, S, ctl, fused)
+                        : launch_rollout_a<kA, false>(c, eps, U, prob, S, ctl, fused));
     return cudaSuccess;
 }
 
 cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev *prob,
-                           const CtlDev *ctl, float *wt, float *eta_part)
+                           const CtlDev *ctl, float *wt, long long *acc)
 {
     weights_kernel<<<c.weights_blocks, 256, 0, c.stream>>>(S, (long long)c.k_local,
                                                            (long long)c.k_pad, prob, ctl, wt,
-                                                           eta_part);
+                                                           acc + c.rows);
     return cudaGetLastError();
 }
 
 cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *wt,
-                           float *partials)
+                           long long *acc)
 {
     const size_t smem = average_smem_bytes(c.rows);
     const int nslab = (int)(c.k_pad / kAvgTileK);
     const int nchunk = (c.rows + kAvgTileR - 1) / kAvgTileR;
-    average_kernel<<<c.avg_grid, kAvgThreads, smem, c.stream>>>(tmap_eps, wt, partials, c.avg_gpad,
-                                                                c.rows, nslab, nchunk);
+    average_kernel<<<c.avg_grid, kAvgThreads, smem, c.stream>>>(tmap_eps, wt, acc, c.rows, nslab,
+                                                                nchunk);
     return cudaGetLastError();
 }
 
-cudaError_t launch_finalize(const LaunchCtx &c, bool fold, bool update, const float *partials,
-                            const float *eta_part, float *red, float *U, float *U_prev,
+cudaError_t launch_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
                             const ProblemDev *prob, CtlDev *ctl, float *next_act, unsigned flags)
 {
     const size_t smem = sizeof(float) * (size_t)c.rows;
-#define MPPI_FIN_ARGS partials, c.avg_gpad, c.avg_grid, eta_part, c.weights_blocks, red, U, U_prev, \
-                      prob, ctl, next_act, c.horizon, c.act_dim, flags
-    if (fold && update)
-        finalize_kernel<true, true><<<1, kFinThreads, smem, c.stream>>>(MPPI_FIN_ARGS);
-    else if (fold)
-        finalize_kernel<true, false><<<1, kFinThreads, smem, c.stream>>>(MPPI_FIN_ARGS);
-    else if (update)
-        finalize_kernel<false, true><<<1, kFinThreads, smem, c.stream>>>(MPPI_FIN_ARGS);
-    else
-        return cudaErrorInvalidValue;
-#undef MPPI_FIN_ARGS
+    finalize_kernel<<<1, kFinThreads, smem, c.stream>>>(acc, U, U_prev, prob, ctl, next_act,
+                                                        c.horizon, c.act_dim, flags);
     return cudaGetLastError();
 }
 
@@ -690,21 +741,27 @@ cudaError_t launch_trajectories(const LaunchCtx &c, const float *eps, const floa
 }
 
 // Per-device one-time opt-in to large dynamic shared memory (called from mppi_create).
+template <int A, bool STRICT>
+static cudaError_t configure_rollout_s(int smem)
+{
+    cudaError_t e;
+    e = cudaFuncSetAttribute(rollout_kernel<A, STRICT, true, 4>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rollout_kernel<A, STRICT, false, 4>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rollout_kernel<A, STRICT, false, 2>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(rollout_kernel<A, STRICT, false, 1>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
 template <int A>
 static cudaError_t configure_rollout(int smem)
 {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(rollout_kernel<A, true, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rollout_kernel<A, true, false>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rollout_kernel<A, false, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(rollout_kernel<A, false, false>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = configure_rollout_s<A, true>(smem);
+    return e != cudaSuccess ? e : configure_rollout_s<A, false>(smem);
 }
 
 cudaError_t configure_kernels(const LaunchCtx &c)
@@ -715,14 +772,10 @@ cudaError_t configure_kernels(const LaunchCtx &c)
     if (e != cudaSuccess) return e;
     const int fin = (int)(sizeof(float) * (size_t)c.rows);
     if (fin > 48 * 1024) {
-        e = cudaFuncSetAttribute(finalize_kernel<true, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(finalize_kernel<false, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
+        e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
         if (e != cudaSuccess) return e;
     }
-    const int ro = (int)(2 * sizeof(float) * (size_t)c.rows);
+    const int ro = (int)(sizeof(float) * (size_t)c.horizon * 8);
     if (ro > 48 * 1024) {
         MPPI_DISPATCH_A(c.act_dim, e = configure_rollout<kA>(ro));
         if (e != cudaSuccess) return e;

@@ -2,6 +2,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace mppi {
 
@@ -28,29 +29,29 @@ struct LaunchCtx {
     bool strict;           // MPPI_FLAG_STRICT_ARITH
     int  num_sms;
     int  avg_grid;         // CTAs of the averaging kernel
-    int  avg_gpad;         // leading dimension of the per-CTA partials (multiple of 32)
-    int  weights_blocks;   // CTAs of the weights kernel == number of eta partials
+    int  weights_blocks;   // CTAs of the weights kernel
+    int  rollout_spt;      // samples per thread in the rollout kernel (1, 2 or 4)
+    SamplerParams sampler; // Philox round keys of the seed, sigma-derived constants
 };
 
 // (1) eps[r][k] = sigma[a] * N(0,1), Philox counter (k/4, r, step)
-cudaError_t launch_sample(const LaunchCtx &c, float *eps, const ProblemDev *prob, const CtlDev *ctl,
+cudaError_t launch_sample(const LaunchCtx &c, float *eps, const CtlDev *ctl,
                           bool use_step_override, unsigned long long step_override);
 
 // (2) S[k] = rollout cost; block min -> atomicMin(ctl->min_key).  fused: also samples eps.
 cudaError_t launch_rollout(const LaunchCtx &c, float *eps, const float *U, const ProblemDev *prob,
                            float *S, CtlDev *ctl, bool fused_sampling);
 
-// (3) wt[k] = expf(-(1/lambda)(S[k]-beta)), eta_part[block] = sum
+// (3) wt[k] = expf(-(1/lambda)(S[k]-beta)), acc[R] += eta partial (fixed point)
 cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev *prob,
-                           const CtlDev *ctl, float *wt, float *eta_part);
+                           const CtlDev *ctl, float *wt, long long *acc);
 
-// (4) partials[r][cta] = sum_{k in cta's tiles} wt[k] * eps[r][k]
+// (4) acc[r] += sum_{k in cta's tiles} wt[k] * eps[r][k]   (fixed point, r < R)
 cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *wt,
-                           float *partials);
+                           long long *acc);
 
-// (5) fold partials (+eta) -> red[0..R] ; update U, shift, next_act, advance step
-cudaError_t launch_finalize(const LaunchCtx &c, bool fold, bool update, const float *partials,
-                            const float *eta_part, float *red, float *U, float *U_prev,
+// (5) U += acc[0..R-1]/acc[R]; shift, next_act, advance step, re-arm acc and min key
+cudaError_t launch_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
                             const ProblemDev *prob, CtlDev *ctl, float *next_act, unsigned flags);
 
 // layout conversion between the reference's [K][T*A] and the internal K-minor [T*A][k_pad]

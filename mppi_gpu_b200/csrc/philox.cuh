@@ -7,8 +7,8 @@
 //
 //     quad q = k_global / 4, row r = t*A + a, control step s
 //     (x0,x1,x2,x3) = Philox4x32-10(counter = {q, r, s_lo, s_hi}, key = {seed_lo, seed_hi})
-//     (n0,n1) = BoxMuller(x0,x1), (n2,n3) = BoxMuller(x2,x3)
-//     eps[k = 4q+j, t, a] = sigma[a] * n_j
+//     (e0,e1) = BoxMuller(x0,x1; sigma_a), (e2,e3) = BoxMuller(x2,x3; sigma_a)
+//     eps[k = 4q+j, t, a] = e_j                    (a = r mod A)
 //
 // One Philox call yields the float4 of four consecutive samples in one row of the K-minor
 // eps layout, so the store is a single 16-byte vector store and the value of eps[k,t,a]
@@ -25,55 +25,83 @@ constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
 constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+// Host-precomputed sampler constants, passed to the kernels by value (constant bank):
+// the ten Philox round keys of the seed and, per action dim, c[a] = -2 ln2 * sigma_a^2 so
+// that sigma * sqrt(-2 ln u) = sqrt(c[a] * log2 u) costs one FMUL + one MUFU.
+struct SamplerParams {
+    uint32_t k0[10], k1[10];
+    float c[kMaxAct];
+};
+
+inline SamplerParams make_sampler_params(unsigned long long seed, const float *sigma, int A)
+{
+    SamplerParams sp{};
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int i = 0; i < 10; ++i) { sp.k0[i] = a; sp.k1[i] = b; a += kPhiloxW0; b += kPhiloxW1; }
+    for (int i = 0; i < A; ++i) sp.c[i] = -1.3862943611198906f * (sigma[i] * sigma[i]);
+    return sp;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const SamplerParams &sp)
 {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         const uint32_t hi0 = __umulhi(kPhiloxM0, c.x), lo0 = kPhiloxM0 * c.x;
         const uint32_t hi1 = __umulhi(kPhiloxM1, c.z), lo1 = kPhiloxM1 * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += kPhiloxW0;
-        k.y += kPhiloxW1;
+        c = make_uint4(hi1 ^ c.y ^ sp.k0[i], lo1, hi0 ^ c.w ^ sp.k1[i], lo0);
     }
     return c;
 }
 
-// uniform in (0,1]: x*2^-32 + 2^-33 as one fused op
-__device__ __forceinline__ float u01(uint32_t x)
+__device__ __forceinline__ float mufu_lg2(float x)
 {
-    return __fmaf_rn(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
-
-__device__ __forceinline__ float sqrt_approx(float x)
+__device__ __forceinline__ float mufu_sqrt(float x)
 {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-
-// two N(0,1) values from two 32-bit draws; MUFU.LG2 / MUFU.SQRT / MUFU.SIN / MUFU.COS
-__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float &n0, float &n1)
+__device__ __forceinline__ float mufu_sin(float x)
 {
-    const float u = u01(xa);
-    const float v = u01(xb);
-    // -2 ln(u) = (-2 ln 2) * log2(u)
-    const float r = sqrt_approx(-1.3862943611198906f * __log2f(u));
-    float s, c;
-    __sincosf(6.283185307179586f * v, &s, &c);
-    n0 = r * s;
-    n1 = r * c;
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_cos(float x)
+{
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
-// the four standard normals of (quad q, row r, step, seed)
-__device__ __forceinline__ float4 normal4(uint32_t q, uint32_t r, unsigned long long step,
-                                          unsigned long long seed)
+// Box-Muller on two 32-bit draws, already scaled by sigma (through c = -2 ln2 sigma^2):
+//   u     = xa*2^-32 + 2^-33            in (0,1]
+//   theta = xb*2pi*2^-32 + 2pi*2^-33    in (0,2pi]
+//   r     = sqrt(|c * log2 u|)          (|.|: MUFU.LG2 may return +tiny for u -> 1)
+__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float c, float &n0, float &n1)
 {
-    const uint4 x = philox4x32_10(make_uint4(q, r, (uint32_t)step, (uint32_t)(step >> 32)),
-                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float u  = __fmaf_rn(__uint2float_rn(xa), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float th = __fmaf_rn(__uint2float_rn(xb), 1.4629180792671596e-9f, 7.314590396335798e-10f);
+    const float r  = mufu_sqrt(fabsf(__fmul_rn(c, mufu_lg2(u))));
+    n0 = __fmul_rn(r, mufu_sin(th));
+    n1 = __fmul_rn(r, mufu_cos(th));
+}
+
+// eps of (quad q, row r, step) for the four samples 4q..4q+3, c = sp.c[a] of that row
+__device__ __forceinline__ float4 sample4(uint32_t q, uint32_t r, unsigned long long step,
+                                          const SamplerParams &sp, float c)
+{
+    const uint4 x = philox4x32_10(make_uint4(q, r, (uint32_t)step, (uint32_t)(step >> 32)), sp);
     float4 n;
-    box_muller(x.x, x.y, n.x, n.y);
-    box_muller(x.z, x.w, n.z, n.w);
+    box_muller(x.x, x.y, c, n.x, n.y);
+    box_muller(x.z, x.w, c, n.z, n.w);
     return n;
 }
+#endif  // __CUDACC__
 
 }  // namespace mppi

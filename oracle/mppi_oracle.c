@@ -275,19 +275,17 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* uniform in (0,1]: x*2^-32 + 2^-33, one fused op (as the device code does) */
-static inline float u01(uint32_t x)
+/* Box-Muller on a pair of 32-bit draws -> two N(0, sigma^2) values (sin first), the
+ * same formulation as the device code (mppi_gpu_b200/csrc/philox.cuh):
+ *   u     = xa*2^-32 + 2^-33           in (0,1]   (one fused op)
+ *   theta = xb*2pi*2^-32 + 2pi*2^-33   in (0,2pi] (one fused op)
+ *   r     = sqrt(|c * log2 u|),  c = -2 ln2 * sigma^2  (float ops)
+ * libm log2f/sqrtf/sinf/cosf here, MUFU approximations on the device. */
+static inline void box_muller(uint32_t xa, uint32_t xb, float c, float *n0, float *n1)
 {
-    return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-}
-
-/* Box-Muller on a pair of 32-bit draws -> two N(0,1) values (sin first) */
-static inline void box_muller(uint32_t xa, uint32_t xb, float *n0, float *n1)
-{
-    float u = u01(xa);
-    float v = u01(xb);
-    float r = sqrtf(-2.0f * logf(u));
-    float th = 6.283185307179586f * v;
+    float u  = fmaf((float)xa, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    float th = fmaf((float)xb, 1.4629180792671596e-9f, 7.314590396335798e-10f);
+    float r  = sqrtf(fabsf(c * log2f(u)));
     *n0 = r * sinf(th);
     *n1 = r * cosf(th);
 }
@@ -297,6 +295,8 @@ void oracle_sample_eps(uint64_t seed, uint64_t step, int64_t k0, int64_t K, int 
 {
     const int R = T * A;
     const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    float c[ORACLE_MAX_ACT];
+    for (int a = 0; a < A; a++) c[a] = -1.3862943611198906f * (sigma[a] * sigma[a]);
     for (int64_t k = 0; k < K; k++) {
         const int64_t kg = k0 + k;
         const uint32_t q = (uint32_t)(kg >> 2);
@@ -306,9 +306,9 @@ void oracle_sample_eps(uint64_t seed, uint64_t step, int64_t k0, int64_t K, int 
             uint32_t x[4];
             float n[4];
             oracle_philox4x32_10(ctr, key, x);
-            box_muller(x[0], x[1], &n[0], &n[1]);
-            box_muller(x[2], x[3], &n[2], &n[3]);
-            eps[(size_t)k * R + r] = sigma[r % A] * n[lane];
+            box_muller(x[0], x[1], c[r % A], &n[0], &n[1]);
+            box_muller(x[2], x[3], c[r % A], &n[2], &n[3]);
+            eps[(size_t)k * R + r] = n[lane];
         }
     }
 }

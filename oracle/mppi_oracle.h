@@ -94,8 +94,8 @@ void  oracle_step(const oracle_problem *p, const float *x0, float *U,
 void  oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
 /* The controller's noise stream: for quad q = k/4 and row r = t*A+a,
- *   (n0..n3) = BoxMuller(Philox(ctr = {q, r, step_lo, step_hi}, key = seed))
- *   eps[k=4q+j, t, a] = sigma[a] * n_j
+ *   (e0..e3) = BoxMuller(Philox(ctr = {q, r, step_lo, step_hi}, key = seed); sigma[a])
+ *   eps[k=4q+j, t, a] = e_j
  * Writes the reference layout [K,T,A] for global samples k0 .. k0+K-1. */
 void  oracle_sample_eps(uint64_t seed, uint64_t step, int64_t k0, int64_t K, int T, int A,
                         const float *sigma, float *eps);

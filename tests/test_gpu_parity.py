@@ -22,8 +22,9 @@ RTOL_U = 1e-5
 
 
 def _close(a, b, tol=RTOL_U):
-    a = np.asarray(a, np.float64)
-    b = np.asarray(b, np.float64)
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    assert a.shape == b.shape, (a.shape, b.shape)
     return np.all(np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b)))
 
 
@@ -64,7 +65,7 @@ def _assert_parity(next_act, inf, info, ref, K, T, A):
     assert abs(float(inf["weight"].astype(np.float64).sum()) - 1.0) < 1e-4
     # (4) U (post shift) and next action
     assert _close(inf["u"].ravel(), ref["U"]), \
-        f"max |dU| = {np.abs(inf['u'].ravel() - ref['U']).max()}"
+        f"max |dU| = {np.abs(inf['u'].ravel() - ref['U'].ravel()).max()}"
     assert _close(next_act, ref["next_act"])
     # noise tap returns exactly what was injected, in the reference layout
     assert inf["e"].shape == (K, T, A)
@@ -149,35 +150,53 @@ def test_reference_update_act_fixture(M, oracle):
     _assert_parity(next_act, inf, info, ref, K, T, A)
 
 
-def test_multi_step_receding_horizon(M, oracle):
-    """20 control steps with fresh injected noise and a moving state: U, shift and the
-    step counter stay in lock-step with the oracle (get_act + set_x loop, src/main.cu:326-371)."""
-    K, T, A = 1000, 40, 2
+def _plant(x, act, g, b, A):
+    """ideal double integrator (the model of src/model_missmatch.cpp:26-38)"""
+    pos, vel = x[:A].astype(np.float32), x[A:].astype(np.float32)
+    act = np.asarray(act, np.float32)
+    return np.concatenate([pos + g[1] * vel + b[0] * act, vel + b[1] * act]).astype(np.float32)
+
+
+def test_closed_loop_200_steps_tracks_oracle(M, oracle):
+    """Receding-horizon loop of src/main.cu:326-371 (get_u, get_act, plant, set_x) for 200
+    control steps on identical injected noise.
+      * per step, from the GPU's own (x, U): next action / U' within 1e-5, argmin exact;
+      * free-running: the GPU loop and an independent oracle loop (own plant copy, own U)
+        stay within CLOSED_LOOP_TOL = 1e-3 * max(1, |x|) in state over all 200 steps."""
+    CLOSED_LOOP_TOL = 1e-3
+    K, T, A = 512, 30, 2
     cfg = REF_CFG[A]
     rs = np.random.RandomState(5)
     ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, flags=1)
-    x = np.zeros(4, np.float32)
+    x_gpu = np.zeros(4, np.float32)
+    x_orc = x_gpu.copy()
     U0 = np.zeros((T, A), np.float32)
-    ctl.memcpy_set_data(x, U0, cfg["goal"], cfg["w"])
+    ctl.memcpy_set_data(x_gpu, U0, cfg["goal"], cfg["w"])
     p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"])
-    Uo = U0.ravel().copy()
+    U_orc = U0.copy()
     g, b = oracle.gains(0.1)
-    for step in range(20):
+    worst = 0.0
+    for step in range(200):
         eps = (0.25 * rs.standard_normal((K, T, A))).astype(np.float32)
         ctl.set_noise(eps)
-        pre = ctl.get_u()
-        assert _close(pre.ravel(), Uo)
-        na = ctl.get_act()
-        ref = oracle.step(p, x, Uo, eps)
-        assert _close(na, ref["next_act"])
-        assert ctl.step_info()["argmin"] == ref["argmin"]
-        assert ctl.step_info()["step"] == step + 1
-        Uo = ref["U"]
-        # plant: the ideal double integrator driven by the GPU's action
-        pos, vel = x[:A].copy(), x[A:].copy()
-        x = np.concatenate([pos + g[1] * vel + b[0] * na, vel + b[1] * na]).astype(np.float32)
-        ctl.set_x(x)
-    assert _close(ctl.get_u().ravel(), Uo, tol=1e-4)
+        pre = ctl.get_u()                              # main.cu:327
+        na = ctl.get_act()                             # main.cu:330
+        info = ctl.step_info()
+        one = oracle.step(p, x_gpu, pre, eps)          # same state, same U, same noise
+        assert _close(na, one["next_act"])
+        assert info["argmin"] == one["argmin"] and info["step"] == step + 1
+        assert _close(ctl.get_u(), one["U"])
+        free = oracle.step(p, x_orc, U_orc, eps)       # independent oracle loop
+        U_orc = free["U"]
+        x_gpu = _plant(x_gpu, na, g, b, A)
+        x_orc = _plant(x_orc, free["next_act"], g, b, A)
+        err = np.max(np.abs(x_gpu - x_orc) / np.maximum(1.0, np.abs(x_orc)))
+        worst = max(worst, float(err))
+        assert err <= CLOSED_LOOP_TOL, (step, err)
+        ctl.set_x(x_gpu)                               # main.cu:371
+    # the controller actually drove the mass towards the goal position (1, 0)
+    assert x_gpu[0] > 0.4 and abs(x_gpu[1]) < 0.2, x_gpu
+    print("closed loop worst relative state deviation:", worst)
     ctl.close()
 
 

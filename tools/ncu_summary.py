@@ -1,0 +1,44 @@
+"""Summarise an `ncu --page raw --csv` dump: one block of key metrics per profiled kernel."""
+import csv
+import sys
+
+WANT = [
+    'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+    'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+    'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+    'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+    'launch__occupancy_limit_registers', 'launch__grid_size', 'launch__block_size',
+    'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+    'smsp__issue_active.avg.pct_of_peak_sustained_active',
+    'smsp__inst_executed.sum', 'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum',
+    'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+    'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_drain_per_issue_active.ratio',
+]
+
+
+def main(path):
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index('Kernel Name')
+    for r in rows[2:]:
+        print('---- ' + r[ki][:90])
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                print(f"  {w:82s} {r[i]:>18s} {units[i]}")
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])
