@@ -1,0 +1,148 @@
+// mppi_main.cpp -- the reference's driver loop (src/main.cu:220-399) on the B200 core.
+//
+//   mppi_main -c <config.yaml> [-t traj.csv] [--plant ideal|mjcf] [--steps N] [--samples K]
+//             [--horizon T] [--honour-config] [--seed S] [--verify-config] [--quiet]
+//
+// Same sequence as the reference: parse config, build the plant and the controller, get_x,
+// zero action sequence, memcpy_set_data, then loop { get_u; time(get_act); simulate; get_x;
+// record; set_x } until the plant says done, print "Average controller execution time", write
+// the trajectory CSV in the reference's format (to_csv_traj, src/main.cu:32-57; header
+// x,y,vx,vy,ux,uy,size_x,size_u for 2-D, generalised to x0..,v0..,u0.. otherwise).
+// The controller is the reference's class name, provided by the shim header.
+//
+// --honour-config passes lambda / noise / init-act / max-a to the controller (the reference
+// parses and drops them, src/main.cu:311); without it the reference-compatible preset runs.
+// --verify-config restates the reference's parser self-test (src/main.cu:295-307,686-725) and
+// needs no GPU.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../include/mppi_b200/point_mass.hpp"
+#include "config.hpp"
+#include "plant.hpp"
+
+typedef std::chrono::steady_clock Clock;
+
+static void to_csv_traj(const std::string &filename, const std::vector<std::vector<float>> &x,
+                        const std::vector<std::vector<float>> &u, int A)
+{
+    std::ofstream out(filename);
+    std::cout << "Saving traj to file...: " << std::endl;
+    static const char *axes[] = {"x", "y", "z", "w"};
+    for (int i = 0; i < A; ++i) out << axes[i] << ",";
+    for (int i = 0; i < A; ++i) out << "v" << axes[i] << ",";
+    for (int i = 0; i < A; ++i) out << "u" << axes[i] << ",";
+    out << "size_x,size_u" << std::endl;
+    for (size_t r = 0; r < u.size(); ++r) {
+        for (int i = 0; i < 2 * A; ++i) out << x[r][i] << ",";
+        for (int i = 0; i < A; ++i) out << u[r][i] << (i + 1 < A || r == 0 ? "," : "");
+        if (r == 0) out << x.size() << "," << u.size();
+        out << std::endl;
+    }
+    for (int i = 0; i < 2 * A; ++i) out << x[u.size()][i] << (i + 1 < 2 * A ? "," : "");
+    out.close();
+    std::cout << x.size() << " " << u.size() << std::endl;
+}
+
+int main(int argc, char **argv)
+{
+    std::string config_file = "config/point_mass2d.yaml", traj_file, plant_name = "ideal";
+    long max_steps = -1, samples_override = -1, horizon_override = -1;
+    bool honour = false, verify = false, quiet = false;
+    unsigned long long seed = 0;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() -> std::string {
+            if (i + 1 >= argc) { std::cerr << "missing value for " << a << std::endl; exit(2); }
+            return argv[++i];
+        };
+        if (a == "-c" || a == "--config") config_file = next();
+        else if (a == "-t" || a == "--traj-save") traj_file = next();
+        else if (a == "--plant") plant_name = next();
+        else if (a == "--steps") max_steps = std::stol(next());
+        else if (a == "--samples") samples_override = std::stol(next());
+        else if (a == "--horizon") horizon_override = std::stol(next());
+        else if (a == "--seed") seed = std::stoull(next());
+        else if (a == "--honour-config") honour = true;
+        else if (a == "--verify-config") verify = true;
+        else if (a == "--quiet") quiet = true;
+        else { std::cerr << "unknown argument " << a << std::endl; return 2; }
+    }
+
+    mppi_cfg::Config cfg = mppi_cfg::parse(config_file);
+    std::cout << "N " << cfg.samples << " steps: " << cfg.horizon << " State dim: " << cfg.state_dim
+              << std::endl;
+    if (verify) {
+        if (!mppi_cfg::verify_test_config(cfg)) { std::cout << "Test FAILED" << std::endl; return 1; }
+        std::cout << "Test passed" << std::endl;
+        return 0;
+    }
+    int n = samples_override > 0 ? (int)samples_override : cfg.samples;
+    int steps = horizon_override > 0 ? (int)horizon_override : cfg.horizon;
+    const int state_dim = cfg.state_dim, act_dim = cfg.act_dim;
+
+    std::vector<float> next_act(act_dim), init_state(state_dim), init_actions((size_t)steps * act_dim, 0.f);
+    std::vector<float> u_prev((size_t)steps * act_dim);
+    std::vector<std::vector<float>> x, u;
+
+    PointMassEnv env(act_dim, plant_name == "mjcf" ? PointMassEnv::kMjcf : PointMassEnv::kIdeal,
+                     cfg.dt, max_steps > 0 ? 1e30 : 10.0);
+
+    PointMassModel::Options opt;
+    opt.seed = seed;
+    if (honour) {
+        opt.lambda = cfg.lambda;
+        opt.sigma = cfg.noise.data();
+        opt.init_act = cfg.init_act.data();
+        opt.max_act = cfg.max_a.data();
+    }
+    PointMassModel *model = new PointMassModel(n, steps, cfg.dt, state_dim, act_dim, false, opt);
+
+    env.get_x(init_state.data());
+    model->memcpy_set_data(init_state.data(), init_actions.data(), cfg.goal.data(), cfg.cost_w.data());
+    x.push_back(init_state);
+
+    std::vector<double> lat_ms;
+    bool done = false;
+    long t = 0;
+    while (!done) {
+        model->get_u(u_prev.data());
+        auto t1 = Clock::now();
+        model->get_act(next_act.data());
+        auto t2 = Clock::now();
+        lat_ms.push_back(std::chrono::duration<double, std::milli>(t2 - t1).count());
+        if (!quiet) {
+            std::cout << "next_act: ";
+            for (int i = 0; i < act_dim; i++) std::cout << next_act[i] << " ";
+            std::cout << std::endl;
+        }
+        done = env.simulate(next_act.data());
+        env.get_x(init_state.data());
+        u.push_back(next_act);
+        x.push_back(init_state);
+        model->set_x(init_state.data());
+        t += 1;
+        if (max_steps > 0 && t >= max_steps) done = true;
+    }
+    double total = 0;
+    for (double v : lat_ms) total += v;
+    std::vector<double> sorted = lat_ms;
+    std::sort(sorted.begin(), sorted.end());
+    std::cout << "Average controller execution time: " << total / t << std::endl;
+    std::cout << "T: " << t << std::endl;
+    std::cout << "Delta: " << total << std::endl;
+    std::cout << "latency_ms p50: " << sorted[sorted.size() / 2]
+              << " p99: " << sorted[std::min(sorted.size() - 1, (size_t)(0.99 * sorted.size()))]
+              << " rollout-steps/s: " << (double)n * steps / (total / t * 1e-3) << std::endl;
+    std::cout << "final state:";
+    for (int i = 0; i < state_dim; ++i) std::cout << " " << init_state[i];
+    std::cout << std::endl;
+    if (!traj_file.empty()) to_csv_traj(traj_file, x, u, act_dim);
+    delete model;
+    return 0;
+}

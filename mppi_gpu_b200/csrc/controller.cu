@@ -66,7 +66,8 @@ struct mppi_handle {
     int stage_slot = 0;
     float *h_next = nullptr;      // pinned [kMaxAct]
 
-    CUtensorMap tmap{};
+    CUtensorMap tmap{};        // average kernel: box {256, kAvgTileR}
+    CUtensorMap tmap_ro{};     // TMA rollout: box {256, TT*A}
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // [0] sampling, [1] injected noise
     NcclComm comm;
 
@@ -87,7 +88,7 @@ namespace {
 bool multi(const mppi_handle *h) { return h->p.world_size > 1; }
 bool fused(const mppi_handle *h) { return (h->p.flags & MPPI_FLAG_FUSED_SAMPLING) != 0; }
 
-int encode_tmap(mppi_handle *h)
+int encode_tmap(mppi_handle *h, CUtensorMap *out, int box_rows)
 {
     typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                     const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -100,10 +101,10 @@ int encode_tmap(mppi_handle *h)
         return fail(MPPI_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
     const cuuint64_t gdim[2] = {(cuuint64_t)h->ctx.k_pad, (cuuint64_t)h->R};
     const cuuint64_t gstride[1] = {(cuuint64_t)h->ctx.k_pad * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kAvgTileK, (cuuint32_t)kAvgTileR};
+    const cuuint32_t box[2] = {(cuuint32_t)kAvgTileK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = reinterpret_cast<EncodeTiled>(fn)(
-        &h->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->d_eps, gdim, gstride, box, estr,
+        out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->d_eps, gdim, gstride, box, estr,
         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MPPI_ERR_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
@@ -123,7 +124,10 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
     CK(mark());
     if (sample && !fused(h)) CK(launch_sample(c, h->d_eps, h->d_ctl, false, 0));
     CK(mark());
-    CK(launch_rollout(c, h->d_eps, h->d_U, h->d_prob, h->d_S, h->d_ctl, sample && fused(h)));
+    if (c.rollout_tma && !(sample && fused(h)))
+        CK(launch_rollout_tma(c, h->tmap_ro, h->d_U, h->d_prob, h->d_S, h->d_ctl));
+    else
+        CK(launch_rollout(c, h->d_eps, h->d_U, h->d_prob, h->d_S, h->d_ctl, sample && fused(h)));
     CK(mark());
     if (multi(h)) {
         if (!h->comm.allreduce_min_u64(&h->d_ctl->min_key, 1, c.stream, err))
@@ -310,6 +314,8 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     {
         const double waves4 = (double)c.k_pad / 4.0 / (512.0 * c.num_sms);
         c.rollout_spt = waves4 >= 8.0 ? 4 : (waves4 >= 2.0 ? 2 : 1);
+        c.rollout_tma = false;
+        if (const char *env = getenv("MPPI_ROLLOUT_TMA")) c.rollout_tma = atoi(env) != 0;
         if (const char *env = getenv("MPPI_ROLLOUT_SPT")) {
             const int v = atoi(env);
             if (v == 1 || v == 2 || v == 4) c.rollout_spt = v;
@@ -374,7 +380,8 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
         pd.max_act[a] = p.max_act[a];
     }
     if ((rc = upload_problem(h)) != MPPI_OK) { mppi_destroy(h); return rc; }
-    if ((rc = encode_tmap(h)) != MPPI_OK) { mppi_destroy(h); return rc; }
+    if ((rc = encode_tmap(h, &h->tmap, kAvgTileR)) != MPPI_OK) { mppi_destroy(h); return rc; }
+    if ((rc = encode_tmap(h, &h->tmap_ro, rollout_tma_rows(p.act_dim))) != MPPI_OK) { mppi_destroy(h); return rc; }
 
     if (multi(h)) {
         std::string err;

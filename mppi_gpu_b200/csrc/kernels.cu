@@ -298,6 +298,140 @@ rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
     }
 }
 
+// ---------------------------------------------------------------------------------
+// (2b) TMA-staged rollout.  Same arithmetic, different data path: a producer warp streams
+//      [TT time steps x A rows x 256 samples] eps tiles into a shared-memory ring with
+//      cp.async.bulk.tensor.2d; 256 consumer threads (one sample each) read their column
+//      conflict-free.  No eps registers and no global-load latency on the dependent chain:
+//      three CTAs fit per SM, and for small K (latency-bound) a step costs ~the FP32 chain.
+// ---------------------------------------------------------------------------------
+template <int A> struct RolloutTile {
+    static constexpr int kSteps = (A == 1 ? 20 : A == 2 ? 10 : A == 3 ? 7 : 5);   // TT
+    static constexpr int kRows  = kSteps * A;                                     // <= 21
+};
+constexpr int kRtStages = 3;
+constexpr int kRtConsumerWarps = 8;
+constexpr int kRtThreads = (kRtConsumerWarps + 1) * 32;
+
+template <int A>
+size_t rollout_tma_smem_bytes(int T)
+{
+    return (size_t)kRtStages * RolloutTile<A>::kRows * 256 * sizeof(float) +
+           (size_t)T * UStage<A>::kStride * sizeof(float) + 2 * kRtStages * sizeof(uint64_t) + 128;
+}
+
+template <int A, bool STRICT>
+__global__ void __launch_bounds__(kRtThreads, 3)
+rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long long k_local,
+                   int T, const float *__restrict__ U, const ProblemDev *__restrict__ prob,
+                   float *__restrict__ S, CtlDev *__restrict__ ctl, unsigned long long k_offset)
+{
+    constexpr int TT = RolloutTile<A>::kSteps;
+    constexpr int ROWS = RolloutTile<A>::kRows;
+    constexpr int UST = UStage<A>::kStride;
+    constexpr uint32_t kTileBytes = ROWS * 256 * sizeof(float);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    float *s_tile = reinterpret_cast<float *>(base);                          // [stage][ROWS][256]
+    float *s_u = s_tile + (size_t)kRtStages * ROWS * 256;                     // [T][UST]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_u + (size_t)T * UST);
+    uint64_t *empty_bar = full_bar + kRtStages;
+    __shared__ unsigned long long s_key[kRtConsumerWarps];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < T * A; i += blockDim.x) {
+        const float u = U[i];
+        const int t = i / A, a = i - t * A;
+        s_u[t * UST + 2 * a]     = u;
+        s_u[t * UST + 2 * a + 1] = __fmul_rn(u, prob->inv_s[a]);
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int st = 0; st < kRtStages; ++st) {
+            mbar_init(&full_bar[st], 1);
+            mbar_init(&empty_bar[st], kRtConsumerWarps);
+        }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    const int ntile = (T + TT - 1) / TT;
+    unsigned long long key = kMinKeyInit;
+
+    if (warp == kRtConsumerWarps) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_eps);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int slab = blockIdx.x; slab < nslab; slab += gridDim.x)
+                for (int tile = 0; tile < ntile; ++tile) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], kTileBytes);
+                    tma_load_2d(s_tile + (size_t)stage * ROWS * 256, &tmap_eps, slab * 256,
+                                tile * ROWS, &full_bar[stage]);
+                    if (++stage == kRtStages) { stage = 0; phase ^= 1; }
+                }
+        }
+        __syncwarp();
+    } else {
+        PointMass<A, STRICT> m;
+        m.load(prob);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int slab = blockIdx.x; slab < nslab; slab += gridDim.x) {
+            float x[2 * A], c = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 2 * A; ++i) x[i] = prob->x0[i];
+            for (int tile = 0; tile < ntile; ++tile) {
+                mbar_wait(&full_bar[stage], phase);
+                const float *col = s_tile + (size_t)stage * ROWS * 256 + threadIdx.x;
+                const int t0 = tile * TT;
+                if (t0 + TT <= T) {
+#pragma unroll
+                    for (int i = 0; i < TT; ++i) {
+                        float u[A], ui[A], e[A];
+                        UStage<A>::fetch(s_u, t0 + i, u, ui);
+#pragma unroll
+                        for (int a = 0; a < A; ++a) e[a] = col[(i * A + a) * 256];
+                        m.step(x, c, u, ui, e);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < TT; ++i)
+                        if (t0 + i < T) {
+                            float u[A], ui[A], e[A];
+                            UStage<A>::fetch(s_u, t0 + i, u, ui);
+#pragma unroll
+                            for (int a = 0; a < A; ++a) e[a] = col[(i * A + a) * 256];
+                            m.step(x, c, u, ui, e);
+                        }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                if (++stage == kRtStages) { stage = 0; phase ^= 1; }
+            }
+            c = __fadd_rn(c, m.state_cost(x, 0.0f));          // src/point_mass_gpu.cu:116
+            const long long k = (long long)slab * 256 + threadIdx.x;
+            S[k] = c;
+            if (k < k_local) {
+                const unsigned long long kk =
+                    ((unsigned long long)float_to_ordered(c) << 32) |
+                    (unsigned long long)(uint32_t)(k_offset + (unsigned long long)k);
+                key = kk < key ? kk : key;
+            }
+        }
+        key = warp_min_u64(key);
+        if (lane == 0) s_key[warp] = key;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        key = threadIdx.x < kRtConsumerWarps ? s_key[threadIdx.x] : kMinKeyInit;
+        key = warp_min_u64(key);
+        if (threadIdx.x == 0 && key != kMinKeyInit) atomicMin(&ctl->min_key, key);
+    }
+}
+
 // =================================================================================
 // (3) weights: exp_red + sum_red (src/point_mass.cu:510-531, :628-666) in one pass.
 //     wt[k] = expf(-(1/lambda) * (S[k] - beta)); the CTA's eta partial is added to the
@@ -672,6 +806,37 @@ cudaError_t launch_rollout(const LaunchCtx &c, float *eps, const float *U, const
     return cudaSuccess;
 }
 
+template <int A, bool STRICT>
+static cudaError_t launch_rollout_tma_t(const LaunchCtx &c, const CUtensorMap &tmap, const float *U,
+                                        const ProblemDev *prob, float *S, CtlDev *ctl)
+{
+    const int nslab = (int)(c.k_pad / 256);
+    const int grid = nslab < 3 * c.num_sms ? nslab : 3 * c.num_sms;
+    rollout_tma_kernel<A, STRICT><<<grid, kRtThreads, rollout_tma_smem_bytes<A>(c.horizon), c.stream>>>(
+        tmap, nslab, (long long)c.k_local, c.horizon, U, prob, S, ctl,
+        (unsigned long long)c.k_offset);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rollout_tma(const LaunchCtx &c, const CUtensorMap &tmap, const float *U,
+                               const ProblemDev *prob, float *S, CtlDev *ctl)
+{
+    MPPI_DISPATCH_A(c.act_dim,
+        return c.strict ? launch_rollout_tma_t<kA, true>(c, tmap, U, prob, S, ctl)
+                        : launch_rollout_tma_t<kA, false>(c, tmap, U, prob, S, ctl));
+    return cudaSuccess;
+}
+
+int rollout_tma_rows(int A)
+{
+    switch (A) {
+        case 1: return RolloutTile<1>::kRows;
+        case 2: return RolloutTile<2>::kRows;
+        case 3: return RolloutTile<3>::kRows;
+        default: return RolloutTile<4>::kRows;
+    }
+}
+
 cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev *prob,
                            const CtlDev *ctl, float *wt, long long *acc)
 {
@@ -775,6 +940,15 @@ cudaError_t configure_kernels(const LaunchCtx &c)
         e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
         if (e != cudaSuccess) return e;
     }
+    MPPI_DISPATCH_A(c.act_dim,
+        e = cudaFuncSetAttribute(rollout_tma_kernel<kA, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)rollout_tma_smem_bytes<kA>(c.horizon));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(rollout_tma_kernel<kA, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)rollout_tma_smem_bytes<kA>(c.horizon)));
+    if (e != cudaSuccess) return e;
     const int ro = (int)(sizeof(float) * (size_t)c.horizon * 8);
     if (ro > 48 * 1024) {
         MPPI_DISPATCH_A(c.act_dim, e = configure_rollout<kA>(ro));

@@ -31,6 +31,7 @@ struct LaunchCtx {
     int  avg_grid;         // CTAs of the averaging kernel
     int  weights_blocks;   // CTAs of the weights kernel
     int  rollout_spt;      // samples per thread in the rollout kernel (1, 2 or 4)
+    bool rollout_tma;      // use the TMA-staged rollout kernel (injected / unfused sampling)
     SamplerParams sampler; // Philox round keys of the seed, sigma-derived constants
 };
 
@@ -41,6 +42,11 @@ cudaError_t launch_sample(const LaunchCtx &c, float *eps, const CtlDev *ctl,
 // (2) S[k] = rollout cost; block min -> atomicMin(ctl->min_key).  fused: also samples eps.
 cudaError_t launch_rollout(const LaunchCtx &c, float *eps, const float *U, const ProblemDev *prob,
                            float *S, CtlDev *ctl, bool fused_sampling);
+
+// (2b) the same rollout fed by TMA tiles (tensor map with box {256, rollout_tma_rows(A)})
+cudaError_t launch_rollout_tma(const LaunchCtx &c, const CUtensorMap &tmap, const float *U,
+                               const ProblemDev *prob, float *S, CtlDev *ctl);
+int rollout_tma_rows(int A);
 
 // (3) wt[k] = expf(-(1/lambda)(S[k]-beta)), acc[R] += eta partial (fixed point)
 cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev *prob,
