@@ -314,7 +314,9 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     {
         const double waves4 = (double)c.k_pad / 4.0 / (512.0 * c.num_sms);
         c.rollout_spt = waves4 >= 8.0 ? 4 : (waves4 >= 2.0 ? 2 : 1);
-        c.rollout_tma = false;
+        // below ~2 waves of the register-pipelined kernel the step is latency-bound: the
+        // TMA-staged kernel (eps from shared memory, 1 sample per thread) is faster there
+        c.rollout_tma = waves4 < 2.0;
         if (const char *env = getenv("MPPI_ROLLOUT_TMA")) c.rollout_tma = atoi(env) != 0;
         if (const char *env = getenv("MPPI_ROLLOUT_SPT")) {
             const int v = atoi(env);

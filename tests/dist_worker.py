@@ -92,8 +92,8 @@ def nccl_mode():
     assert (ctl.k_offset, ctl.k_local) == (k0, k1 - k0)
     ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
     p = po.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], lam=lam, arith=po.ARITH_FMA)
-    Uo = U.copy()
     for step in range(3):
+        Uo = ctl.get_u()                       # the (replicated) U this step starts from
         na = ctl.get_act()
         inf = ctl.get_inf()
         info = ctl.step_info()
@@ -127,7 +127,6 @@ def nccl_mode():
         dist.all_gather(u_all, torch.from_numpy(inf["u"].ravel()).cuda())
         for u in u_all[1:]:
             assert torch.equal(u, u_all[0])
-        Uo = ref["U"]
     ctl.close()
     dist.barrier()
     if rank == 0:

@@ -280,21 +280,17 @@ def test_sampled_step_is_self_consistent(M, oracle, fused):
     ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=42,
                            flags=capi.FLAG_FUSED_SAMPLING if fused else 0)
     ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
-    outs = []
+    p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], arith=oracle.ARITH_FMA)
     for step in range(3):
+        pre = ctl.get_u()                       # the U this step starts from (GPU's own)
         na = ctl.get_act()
         inf = ctl.get_inf()
         info = ctl.step_info()
-        outs.append((na, inf, info))
-    ctl.close()
-    p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], arith=oracle.ARITH_FMA)
-    Uo = U.ravel().copy()
-    for step, (na, inf, info) in enumerate(outs):
-        ref = oracle.step(p, x0, Uo, inf["e"])
+        ref = oracle.step(p, x0, pre, inf["e"])
         _assert_parity(na, inf, info, ref, K, T, A)
-        Uo = ref["U"]
         want = oracle.sample_eps(42, step, 0, K, T, A, [0.025] * A)
         _assert_noise_close(inf["e"], want, 0.025)
+    ctl.close()
     # fused and unfused sampling draw the same noise: checked through the oracle stream above
 
 
