@@ -204,7 +204,12 @@ def run_ours(args, name, K, T, A, dt, goal, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    flags = args.flags
+    # chain selection: with >= 4e5 samples per GPU the fused sample+rollout kernel (one pass
+    # writes eps and integrates; identical eps values) beats the separate sampling kernel;
+    # below that the step is latency-bound and the 4-part chain with the TMA rollout wins.
+    k_loc = capi.shard_range(K, rank, world)
+    k_loc = k_loc[1] - k_loc[0]
+    flags = args.flags if args.flags >= 0 else (capi.FLAG_FUSED_SAMPLING if k_loc >= 400000 else 0)
     ctl = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=flags, device=local_rank, rank=rank,
                            world_size=world, comm_id=comm_id)
     x0 = np.zeros(2 * A, np.float32)
@@ -299,6 +304,9 @@ def run_ours(args, name, K, T, A, dt, goal, w):
                          % (eps_bytes / 1e6) if eps_bytes > 200e6 else
                          "working set fits L2 (%.0f MB eps): latency-bound config, no flush" % (eps_bytes / 1e6),
                    "flags": flags, "graph": not (flags & capi.FLAG_NO_GRAPH),
+                   "chain": ("sample+rollout(fused) -> weights -> average -> finalize"
+                             if flags & capi.FLAG_FUSED_SAMPLING else
+                             "sample -> rollout -> weights -> average -> finalize"),
                    "timing": "value: CUDA events on the controller stream around K graph launches; "
                              "kernels/roofline: CUDA events between kernels in a second region of K steps"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4 * 2 * A,
@@ -310,9 +318,35 @@ def run_ours(args, name, K, T, A, dt, goal, w):
         "kernels": per_kernel,
         "clocks": clk,
     }
+    if flags & capi.FLAG_FUSED_SAMPLING:
+        # the canonical 4-part chain (separate sampling kernel) timed beside it, same workload
+        ctl.close()
+        ctl = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=flags & ~capi.FLAG_FUSED_SAMPLING,
+                               device=local_rank, rank=rank, world_size=world, comm_id=comm_id) \
+            if world == 1 else None
+        if ctl is not None:
+            ctl.memcpy_set_data(x0, np.zeros((T, A), np.float32), goal, w)
+            for _ in range(3):
+                ctl.get_act()
+            ctl.timer_start()
+            for _ in range(args.steps):
+                ctl.step_enqueue()
+            ms4 = ctl.timer_stop() / args.steps
+            ctl.step_wait()
+            ctl.set_profiling(True)
+            for _ in range(args.steps):
+                ctl.get_act()
+            kt4 = {k: ms / n for k, (ms, n) in ctl.kernel_times().items() if n}
+            ctl.set_profiling(False)
+            out["unfused_4part_chain"] = {
+                "ms_per_step": ms4, "value": K * T / (ms4 * 1e-3),
+                "kernels": {k: ({"ms": v, "hbm_gbs": eps_bytes / (v * 1e-3) / 1e9,
+                                 "hbm_frac": eps_bytes / (v * 1e-3) / 1e9 / peak}
+                                if k in ("sample", "rollout", "average") else {"ms": v})
+                            for k, v in kt4.items()}}
     if world > 1:
         out["collectives_ms"] = {"allreduce_min_u64": kernels.get("comm_min"),
-                                 "fold+allreduce_sum_f32": kernels.get("comm_sum")}
+                                 "allreduce_sum_i64": kernels.get("comm_sum")}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): 1 core, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -330,7 +364,8 @@ def run_ours(args, name, K, T, A, dt, goal, w):
                       f"{os.cpu_count()} host cores present; rollout+cost = "
                       + ("reference sources compiled for the host (oracle/_ref)" if kind == "reference"
                          else "oracle port") + ", reductions/update = oracle port"}
-    ctl.close()
+    if ctl is not None:
+        ctl.close()
     if rank == 0:
         print(json.dumps(out))
     if dist is not None:
@@ -345,7 +380,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--flags", type=int, default=0, help="MPPI_FLAG_* bits (development)")
+    ap.add_argument("--flags", type=int, default=-1,
+                    help="MPPI_FLAG_* bits; default: fused sampling (32) when >= 4e5 samples/GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     K, T, A, dt, goal, w = WORKLOADS[args.workload]

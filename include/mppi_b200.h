@@ -59,6 +59,9 @@ extern "C" {
                                                replaying the captured CUDA graph            */
 #define MPPI_FLAG_FUSED_SAMPLING (1u << 5)  /* sample eps inside the rollout kernel (one pass
                                                writes eps and integrates)                   */
+#define MPPI_FLAG_SPLIT_KERNELS  (1u << 6)  /* run weights (3) and finalize (5) as kernels of
+                                               their own instead of inside the averaging
+                                               kernel (4): per-part profiling                */
 
 /* mppi_params.comm */
 #define MPPI_COMM_NONE  0   /* single shard                                          */

@@ -26,6 +26,7 @@ FLAG_CLAMP_ACTIONS = 1 << 2
 FLAG_REINIT_INIT_ACT = 1 << 3
 FLAG_NO_GRAPH = 1 << 4
 FLAG_FUSED_SAMPLING = 1 << 5
+FLAG_SPLIT_KERNELS = 1 << 6
 
 COMM_NONE, COMM_NCCL = 0, 1
 

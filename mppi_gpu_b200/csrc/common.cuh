@@ -38,7 +38,7 @@ struct CtlDev {
     unsigned long long step;      // control-step counter == Philox counter words 2,3
     unsigned long long last_key;  // min_key of the last finished step (for get_step_info)
     float eta;                    // normaliser of the last finished step
-    float pad_;
+    unsigned int done;            // CTA ticket counter of the merged average+finalize kernel
 };
 
 constexpr unsigned long long kMinKeyInit = ~0ull;

@@ -88,7 +88,7 @@ namespace {
 bool multi(const mppi_handle *h) { return h->p.world_size > 1; }
 bool fused(const mppi_handle *h) { return (h->p.flags & MPPI_FLAG_FUSED_SAMPLING) != 0; }
 
-int encode_tmap(mppi_handle *h, CUtensorMap *out, int box_rows)
+int encode_tmap(mppi_handle *h, CUtensorMap *out, int box_cols, int box_rows)
 {
     typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                     const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -101,7 +101,7 @@ int encode_tmap(mppi_handle *h, CUtensorMap *out, int box_rows)
         return fail(MPPI_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
     const cuuint64_t gdim[2] = {(cuuint64_t)h->ctx.k_pad, (cuuint64_t)h->R};
     const cuuint64_t gstride[1] = {(cuuint64_t)h->ctx.k_pad * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kAvgTileK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = reinterpret_cast<EncodeTiled>(fn)(
         out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->d_eps, gdim, gstride, box, estr,
@@ -134,17 +134,21 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
             return fail(MPPI_ERR_COMM, "%s", err.c_str());
     }
     CK(mark());
-    CK(launch_weights(c, h->d_S, h->d_prob, h->d_ctl, h->d_wt, h->d_acc));
+    const bool split = (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) != 0;
+    if (split) CK(launch_weights(c, h->d_S, h->d_prob, h->d_ctl, h->d_wt, h->d_acc));
     CK(mark());
-    CK(launch_average(c, h->tmap, h->d_wt, h->d_acc));
+    const bool merge_fin = !split && !multi(h);
+    CK(launch_average(c, h->tmap, split ? h->d_wt : h->d_S, h->d_acc, !split, merge_fin, h->d_prob,
+                      h->d_ctl, h->d_U, h->d_Uprev, h->d_next, h->p.flags));
     CK(mark());
     if (multi(h)) {
         if (!h->comm.allreduce_sum_i64(h->d_acc, (size_t)h->R + 1, c.stream, err))
             return fail(MPPI_ERR_COMM, "%s", err.c_str());
     }
     CK(mark());
-    CK(launch_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
-                       h->p.flags));
+    if (!merge_fin)
+        CK(launch_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
+                           h->p.flags));
     CK(cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * h->p.act_dim, cudaMemcpyDeviceToHost,
                        c.stream));
     CK(mark());
@@ -153,8 +157,10 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
 
 int kernels_per_step(const mppi_handle *h, bool sample)
 {
-    int n = 4;                                  // rollout, weights, average, finalize
+    int n = 2;                                  // rollout, average(+weights,+finalize)
     if (sample && !fused(h)) n += 1;            // sampling
+    if (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) n += 2;      // separate weights, finalize
+    else if (multi(h)) n += 1;                  // finalize after the all-reduce
     return n;
 }
 
@@ -262,7 +268,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
                     p.state_dim);
     if (p.samples < 1 || p.samples > 0xffffffffll)
         return fail(MPPI_ERR_INVALID, "samples %lld out of range", (long long)p.samples);
-    if (p.horizon < 1 || (long long)p.horizon * p.act_dim > (1 << 20))
+    if (p.horizon < 1 || (long long)p.horizon * p.act_dim > 32768)
         return fail(MPPI_ERR_INVALID, "horizon %d out of range", p.horizon);
     if (!(p.lambda > 0.0f)) return fail(MPPI_ERR_INVALID, "lambda must be > 0");
     if (p.world_size < 1 || p.rank < 0 || p.rank >= p.world_size)
@@ -318,6 +324,14 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
         // TMA-staged kernel (eps from shared memory, 1 sample per thread) is faster there
         c.rollout_tma = waves4 < 2.0;
         if (const char *env = getenv("MPPI_ROLLOUT_TMA")) c.rollout_tma = atoi(env) != 0;
+        // slab width: keep >= 2 CTAs per SM worth of slabs where K allows
+        c.rollout_tma_width = 256;
+        if (c.k_pad / 256 < 2 * c.num_sms) c.rollout_tma_width = 128;
+        if (c.k_pad / 128 < 2 * c.num_sms) c.rollout_tma_width = 64;
+        if (const char *env = getenv("MPPI_ROLLOUT_TMA_W")) {
+            const int v = atoi(env);
+            if (v == 64 || v == 128 || v == 256) c.rollout_tma_width = v;
+        }
         if (const char *env = getenv("MPPI_ROLLOUT_SPT")) {
             const int v = atoi(env);
             if (v == 1 || v == 2 || v == 4) c.rollout_spt = v;
@@ -382,8 +396,8 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
         pd.max_act[a] = p.max_act[a];
     }
     if ((rc = upload_problem(h)) != MPPI_OK) { mppi_destroy(h); return rc; }
-    if ((rc = encode_tmap(h, &h->tmap, kAvgTileR)) != MPPI_OK) { mppi_destroy(h); return rc; }
-    if ((rc = encode_tmap(h, &h->tmap_ro, rollout_tma_rows(p.act_dim))) != MPPI_OK) { mppi_destroy(h); return rc; }
+    if ((rc = encode_tmap(h, &h->tmap, kAvgTileK, kAvgTileR)) != MPPI_OK) { mppi_destroy(h); return rc; }
+    if ((rc = encode_tmap(h, &h->tmap_ro, c.rollout_tma_width, rollout_tma_rows(p.act_dim))) != MPPI_OK) { mppi_destroy(h); return rc; }
 
     if (multi(h)) {
         std::string err;
@@ -483,8 +497,11 @@ int mppi_step_enqueue(mppi_handle *h)
             for (int i = 0; i < MPPI_K_COUNT; ++i) {
                 float ms = 0.f;
                 CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+                const bool split = (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) != 0;
                 const bool ran = (i == MPPI_K_SAMPLE) ? (sample && !fused(h))
-                               : (i == MPPI_K_COMM_MIN || i == MPPI_K_COMM_SUM) ? multi(h) : true;
+                               : (i == MPPI_K_COMM_MIN || i == MPPI_K_COMM_SUM) ? multi(h)
+                               : (i == MPPI_K_WEIGHTS) ? split
+                               : (i == MPPI_K_FINALIZE) ? (split || multi(h)) : true;
                 if (ran) { h->ms_sum[i] += ms; h->launches[i] += 1; }
             }
         }

@@ -310,18 +310,19 @@ template <int A> struct RolloutTile {
     static constexpr int kRows  = kSteps * A;                                     // <= 21
 };
 constexpr int kRtStages = 3;
-constexpr int kRtConsumerWarps = 8;
-constexpr int kRtThreads = (kRtConsumerWarps + 1) * 32;
 
+// W = samples per CTA slab (TMA box width): 256 for throughput, 128/64 when K is so small
+// that 256-wide slabs would leave SMs idle (the step is then bound by the per-sample
+// dependent chain, and fewer warps per SM sub-partition shorten it).
 template <int A>
-size_t rollout_tma_smem_bytes(int T)
+size_t rollout_tma_smem_bytes(int T, int W)
 {
-    return (size_t)kRtStages * RolloutTile<A>::kRows * 256 * sizeof(float) +
+    return (size_t)kRtStages * RolloutTile<A>::kRows * W * sizeof(float) +
            (size_t)T * UStage<A>::kStride * sizeof(float) + 2 * kRtStages * sizeof(uint64_t) + 128;
 }
 
-template <int A, bool STRICT>
-__global__ void __launch_bounds__(kRtThreads, 3)
+template <int A, bool STRICT, int W>
+__global__ void __launch_bounds__(W + 32, (W == 256 ? 3 : W == 128 ? 6 : 8))
 rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long long k_local,
                    int T, const float *__restrict__ U, const ProblemDev *__restrict__ prob,
                    float *__restrict__ S, CtlDev *__restrict__ ctl, unsigned long long k_offset)
@@ -329,11 +330,12 @@ rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long
     constexpr int TT = RolloutTile<A>::kSteps;
     constexpr int ROWS = RolloutTile<A>::kRows;
     constexpr int UST = UStage<A>::kStride;
-    constexpr uint32_t kTileBytes = ROWS * 256 * sizeof(float);
+    constexpr int kRtConsumerWarps = W / 32;
+    constexpr uint32_t kTileBytes = ROWS * W * sizeof(float);
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    float *s_tile = reinterpret_cast<float *>(base);                          // [stage][ROWS][256]
-    float *s_u = s_tile + (size_t)kRtStages * ROWS * 256;                     // [T][UST]
+    float *s_tile = reinterpret_cast<float *>(base);                          // [stage][ROWS][W]
+    float *s_u = s_tile + (size_t)kRtStages * ROWS * W;                     // [T][UST]
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_u + (size_t)T * UST);
     uint64_t *empty_bar = full_bar + kRtStages;
     __shared__ unsigned long long s_key[kRtConsumerWarps];
@@ -368,7 +370,7 @@ rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long
                 for (int tile = 0; tile < ntile; ++tile) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], kTileBytes);
-                    tma_load_2d(s_tile + (size_t)stage * ROWS * 256, &tmap_eps, slab * 256,
+                    tma_load_2d(s_tile + (size_t)stage * ROWS * W, &tmap_eps, slab * W,
                                 tile * ROWS, &full_bar[stage]);
                     if (++stage == kRtStages) { stage = 0; phase ^= 1; }
                 }
@@ -385,7 +387,7 @@ rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long
             for (int i = 0; i < 2 * A; ++i) x[i] = prob->x0[i];
             for (int tile = 0; tile < ntile; ++tile) {
                 mbar_wait(&full_bar[stage], phase);
-                const float *col = s_tile + (size_t)stage * ROWS * 256 + threadIdx.x;
+                const float *col = s_tile + (size_t)stage * ROWS * W + threadIdx.x;
                 const int t0 = tile * TT;
                 if (t0 + TT <= T) {
 #pragma unroll
@@ -393,7 +395,7 @@ rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long
                         float u[A], ui[A], e[A];
                         UStage<A>::fetch(s_u, t0 + i, u, ui);
 #pragma unroll
-                        for (int a = 0; a < A; ++a) e[a] = col[(i * A + a) * 256];
+                        for (int a = 0; a < A; ++a) e[a] = col[(i * A + a) * W];
                         m.step(x, c, u, ui, e);
                     }
                 } else {
@@ -403,7 +405,7 @@ rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long
                             float u[A], ui[A], e[A];
                             UStage<A>::fetch(s_u, t0 + i, u, ui);
 #pragma unroll
-                            for (int a = 0; a < A; ++a) e[a] = col[(i * A + a) * 256];
+                            for (int a = 0; a < A; ++a) e[a] = col[(i * A + a) * W];
                             m.step(x, c, u, ui, e);
                         }
                 }
@@ -412,7 +414,7 @@ rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long
                 if (++stage == kRtStages) { stage = 0; phase ^= 1; }
             }
             c = __fadd_rn(c, m.state_cost(x, 0.0f));          // src/point_mass_gpu.cu:116
-            const long long k = (long long)slab * 256 + threadIdx.x;
+            const long long k = (long long)slab * W + threadIdx.x;
             S[k] = c;
             if (k < k_local) {
                 const unsigned long long kk =
@@ -494,9 +496,65 @@ size_t average_smem_bytes(int R)
     return tiles + wts + rows + bars + 128;   // + alignment slack
 }
 
+// U update + receding-horizon shift from the fixed-point accumulators, executed by ONE CTA
+// (the finalize kernel, or the last CTA of the merged average kernel).  s_u: T*A floats.
+__device__ __forceinline__ void finalize_body(long long *acc, float *__restrict__ U,
+                                              float *__restrict__ U_prev,
+                                              const ProblemDev *__restrict__ prob, CtlDev *ctl,
+                                              float *__restrict__ next_act, int T, int A,
+                                              unsigned flags, float *s_u)
+{
+    const int R = T * A;
+    const int nt = blockDim.x;
+    const volatile long long *vacc = acc;       // written by other CTAs' atomics: read at L2
+    const float eta = acc_to_float(vacc[R]);
+    for (int i = threadIdx.x; i < R; i += nt) {
+        const float u = U[i];
+        float un = u + acc_to_float(vacc[i]) / eta;
+        if (flags & MPPI_FLAG_CLAMP_ACTIONS) {
+            const float m = prob->max_act[i % A];
+            un = fminf(fmaxf(un, -m), m);
+        }
+        U_prev[i] = u;
+        s_u[i] = un;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R; i += nt) {
+        float v;
+        if (i < R - A)                              v = s_u[i + A];
+        else if (flags & MPPI_FLAG_REINIT_INIT_ACT) v = prob->init_act[i - (R - A)];
+        else                                        v = s_u[i];
+        U[i] = v;
+        acc[i] = 0;
+    }
+    if (threadIdx.x < A) next_act[threadIdx.x] = s_u[threadIdx.x];
+    if (threadIdx.x == 0) {
+        acc[R] = 0;
+        ctl->eta = eta;
+        ctl->last_key = ctl->min_key;
+        ctl->min_key = kMinKeyInit;
+        ctl->step = ctl->step + 1;
+        ctl->done = 0;
+    }
+}
+
+struct FinalizeArgs {
+    float *U, *U_prev, *next_act;
+    int T, A;
+    unsigned flags;
+};
+
+// MERGE_W  : src is S; the producer warp turns each slab of costs into weights
+//            (w~ = expf(-(1/lambda)(S-beta)), part 3) while the TMA tile is in flight and adds
+//            the slab's eta once (in the CTA that owns the slab's first tile).
+//            Otherwise src is the weights array written by weights_kernel.
+// MERGE_FIN: the last CTA to finish (ticket from an atomic counter) applies the U update
+//            (part 5) -- single-shard only; multi-shard runs the all-reduce in between.
+template <bool MERGE_W, bool MERGE_FIN>
 __global__ void __launch_bounds__(kAvgThreads, 1)
-average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__restrict__ wt,
-               long long *__restrict__ acc, int rows, int nslab, int nchunk)
+average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__restrict__ src,
+               long long *__restrict__ acc, int rows, int nslab, int nchunk, long long k_local,
+               const ProblemDev *__restrict__ prob, CtlDev *__restrict__ ctl, FinalizeArgs fin)
 {
     extern __shared__ uint8_t smem_raw[];
     // 128-byte aligned carve-up (TMA destinations need 128 B)
@@ -507,6 +565,7 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
     const int rows32 = (rows + 31) / 32 * 32;
     uint64_t *full_bar  = reinterpret_cast<uint64_t *>(s_row + rows32);
     uint64_t *empty_bar = full_bar + kAvgStages;
+    __shared__ int s_last;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -514,7 +573,7 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < kAvgStages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], MERGE_W ? 2 : 1);     // TMA tx (+ the weights arrival)
             mbar_init(&empty_bar[s], kAvgConsumerWarps);
         }
         fence_mbar_init();
@@ -532,21 +591,57 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
 
     if (warp == kAvgConsumerWarps) {
         // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
-            tma_prefetch_desc(&tmap_eps);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (long long t = t_begin; t < t_end; ++t) {
-                const int slab  = (int)(t / nchunk);
-                const int chunk = (int)(t - (long long)slab * nchunk);
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full_bar[stage], kTileBytes + kWtBytes);
+        if (lane == 0) tma_prefetch_desc(&tmap_eps);
+        float beta = 0.f, nil = 0.f, eta_part = 0.f;
+        float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
+        int cur_slab = -1;
+        if (MERGE_W) {
+            beta = ordered_to_float((uint32_t)(ctl->min_key >> 32));
+            nil = prob->neg_inv_lambda;
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long t = t_begin; t < t_end; ++t) {
+            const int slab  = (int)(t / nchunk);
+            const int chunk = (int)(t - (long long)slab * nchunk);
+            if (MERGE_W && slab != cur_slab) {
+                // exp_red (src/point_mass.cu:518) for this lane's 8 samples of the slab
+                const long long k0 = (long long)slab * kAvgTileK + 4 * lane;
+                const float4 sa = *reinterpret_cast<const float4 *>(src + k0);
+                const float4 sb = *reinterpret_cast<const float4 *>(src + k0 + 128);
+                wa.x = (k0 + 0 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(sa.x, beta))) : 0.f;
+                wa.y = (k0 + 1 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(sa.y, beta))) : 0.f;
+                wa.z = (k0 + 2 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(sa.z, beta))) : 0.f;
+                wa.w = (k0 + 3 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(sa.w, beta))) : 0.f;
+                wb.x = (k0 + 128 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(sb.x, beta))) : 0.f;
+                wb.y = (k0 + 129 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(sb.y, beta))) : 0.f;
+                wb.z = (k0 + 130 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(sb.z, beta))) : 0.f;
+                wb.w = (k0 + 131 < k_local) ? expf(__fmul_rn(nil, __fsub_rn(sb.w, beta))) : 0.f;
+                cur_slab = slab;
+            }
+            if (MERGE_W && chunk == 0)       // the slab's eta is counted by exactly one CTA
+                eta_part += ((wa.x + wa.y) + (wa.z + wa.w)) + ((wb.x + wb.y) + (wb.z + wb.w));
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full_bar[stage], MERGE_W ? kTileBytes : kTileBytes + kWtBytes);
                 tma_load_2d(s_tile + (size_t)stage * kAvgTileR * kAvgTileK, &tmap_eps,
                             slab * kAvgTileK, chunk * kAvgTileR, &full_bar[stage]);
-                bulk_load_1d(s_wt + (size_t)stage * kAvgTileK, wt + (size_t)slab * kAvgTileK,
-                             kWtBytes, &full_bar[stage]);
-                if (++stage == kAvgStages) { stage = 0; phase ^= 1; }
+                if (!MERGE_W)
+                    bulk_load_1d(s_wt + (size_t)stage * kAvgTileK, src + (size_t)slab * kAvgTileK,
+                                 kWtBytes, &full_bar[stage]);
             }
+            if (MERGE_W) {
+                float *tw = s_wt + (size_t)stage * kAvgTileK;
+                *reinterpret_cast<float4 *>(tw + 4 * lane) = wa;
+                *reinterpret_cast<float4 *>(tw + 128 + 4 * lane) = wb;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+            }
+            if (++stage == kAvgStages) { stage = 0; phase ^= 1; }
+        }
+        if (MERGE_W) {
+            eta_part = warp_sum(eta_part);
+            if (lane == 0 && eta_part != 0.0f) acc_add(acc + rows, eta_part);
         }
         __syncwarp();
     } else {
@@ -556,12 +651,13 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
         for (long long t = t_begin; t < t_end; ++t) {
             const int slab  = (int)(t / nchunk);
             const int chunk = (int)(t - (long long)slab * nchunk);
+            (void)slab;
             mbar_wait(&full_bar[stage], phase);
             const float *tw = s_wt + (size_t)stage * kAvgTileK;
             const float4 w0 = *reinterpret_cast<const float4 *>(tw + 4 * lane);
             const float4 w1 = *reinterpret_cast<const float4 *>(tw + 128 + 4 * lane);
             const float *tile = s_tile + (size_t)stage * kAvgTileR * kAvgTileK;
-            float acc[kAvgTileR / kAvgConsumerWarps];
+            float a_[kAvgTileR / kAvgConsumerWarps];
 #pragma unroll
             for (int rr = 0; rr < kAvgTileR / kAvgConsumerWarps; ++rr) {
                 const float *row = tile + (size_t)(warp + kAvgConsumerWarps * rr) * kAvgTileK;
@@ -575,18 +671,18 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
                 a = fmaf(e1.y, w1.y, a);
                 a = fmaf(e1.z, w1.z, a);
                 a = fmaf(e1.w, w1.w, a);
-                acc[rr] = a;
+                a_[rr] = a;
             }
             // all shared-memory reads of this stage are done: hand the slot back early
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
 #pragma unroll
-            for (int rr = 0; rr < kAvgTileR / kAvgConsumerWarps; ++rr) acc[rr] = warp_sum(acc[rr]);
+            for (int rr = 0; rr < kAvgTileR / kAvgConsumerWarps; ++rr) a_[rr] = warp_sum(a_[rr]);
             if (lane == 0) {
 #pragma unroll
                 for (int rr = 0; rr < kAvgTileR / kAvgConsumerWarps; ++rr) {
                     const int r = chunk * kAvgTileR + warp + kAvgConsumerWarps * rr;
-                    if (r < rows) s_row[r] += acc[rr];
+                    if (r < rows) s_row[r] += a_[rr];
                 }
             }
             if (++stage == kAvgStages) { stage = 0; phase ^= 1; }
@@ -595,6 +691,21 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
     __syncthreads();
     if (t_end > t_begin)
         for (int r = threadIdx.x; r < rows; r += blockDim.x) acc_add(acc + r, s_row[r]);
+
+    if (MERGE_FIN) {
+        __threadfence();                       // this CTA's atomics before its ticket
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned ticket = atomicAdd(&ctl->done, 1u);
+            s_last = (ticket == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            finalize_body(acc, fin.U, fin.U_prev, prob, ctl, fin.next_act, fin.T, fin.A, fin.flags,
+                          s_tile);             // the tile ring is free now: reuse it for U_new
+        }
+    }
 }
 
 // =================================================================================
@@ -603,6 +714,7 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
 //     sum_red_adim folds, :668-741), next action = U[0,:] (:195), receding-horizon shift with
 //     repeat-last / init-act re-initialisation (shift_act, :805-824), step counter advance,
 //     accumulators and min key re-armed for the next step.  One small CTA.
+//     Single shard: executed by the last CTA of average_kernel (MERGE_FIN) instead.
 //     Multi-shard: acc has been all-reduced (int64 sum, exact) before this kernel.
 // =================================================================================
 constexpr int kFinThreads = 256;
@@ -613,35 +725,7 @@ finalize_kernel(long long *__restrict__ acc, float *__restrict__ U, float *__res
                 float *__restrict__ next_act, int T, int A, unsigned flags)
 {
     extern __shared__ float s_u[];          // U_new [T*A]
-    const int R = T * A;
-    const float eta = acc_to_float(acc[R]);
-    for (int i = threadIdx.x; i < R; i += kFinThreads) {
-        const float u = U[i];
-        float un = u + acc_to_float(acc[i]) / eta;
-        if (flags & MPPI_FLAG_CLAMP_ACTIONS) {
-            const float m = prob->max_act[i % A];
-            un = fminf(fmaxf(un, -m), m);
-        }
-        U_prev[i] = u;
-        s_u[i] = un;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < R; i += kFinThreads) {
-        float v;
-        if (i < R - A)                              v = s_u[i + A];
-        else if (flags & MPPI_FLAG_REINIT_INIT_ACT) v = prob->init_act[i - (R - A)];
-        else                                        v = s_u[i];
-        U[i] = v;
-        acc[i] = 0;
-    }
-    if (threadIdx.x < A) next_act[threadIdx.x] = s_u[threadIdx.x];
-    if (threadIdx.x == 0) {
-        acc[R] = 0;
-        ctl->eta = eta;
-        ctl->last_key = ctl->min_key;
-        ctl->min_key = kMinKeyInit;
-        ctl->step = ctl->step + 1;
-    }
+    finalize_body(acc, U, U_prev, prob, ctl, next_act, T, A, flags, s_u);
 }
 
 // =================================================================================
@@ -742,6 +826,7 @@ __global__ void clear_ctl_kernel(CtlDev *ctl)
     ctl->last_key = kMinKeyInit;
     ctl->step = 0;
     ctl->eta = 0.0f;
+    ctl->done = 0;
 }
 
 // =================================================================================
@@ -806,16 +891,28 @@ cudaError_t launch_rollout(const LaunchCtx &c, float *eps, const float *U, const
     return cudaSuccess;
 }
 
+template <int A, bool STRICT, int W>
+static cudaError_t launch_rollout_tma_w(const LaunchCtx &c, const CUtensorMap &tmap, const float *U,
+                                        const ProblemDev *prob, float *S, CtlDev *ctl)
+{
+    const int nslab = (int)(c.k_pad / W);
+    const int per_sm = (W == 256 ? 3 : W == 128 ? 6 : 8);
+    const int grid = nslab < per_sm * c.num_sms ? nslab : per_sm * c.num_sms;
+    rollout_tma_kernel<A, STRICT, W><<<grid, W + 32, rollout_tma_smem_bytes<A>(c.horizon, W), c.stream>>>(
+        tmap, nslab, (long long)c.k_local, c.horizon, U, prob, S, ctl,
+        (unsigned long long)c.k_offset);
+    return cudaGetLastError();
+}
+
 template <int A, bool STRICT>
 static cudaError_t launch_rollout_tma_t(const LaunchCtx &c, const CUtensorMap &tmap, const float *U,
                                         const ProblemDev *prob, float *S, CtlDev *ctl)
 {
-    const int nslab = (int)(c.k_pad / 256);
-    const int grid = nslab < 3 * c.num_sms ? nslab : 3 * c.num_sms;
-    rollout_tma_kernel<A, STRICT><<<grid, kRtThreads, rollout_tma_smem_bytes<A>(c.horizon), c.stream>>>(
-        tmap, nslab, (long long)c.k_local, c.horizon, U, prob, S, ctl,
-        (unsigned long long)c.k_offset);
-    return cudaGetLastError();
+    switch (c.rollout_tma_width) {
+        case 64:  return launch_rollout_tma_w<A, STRICT, 64>(c, tmap, U, prob, S, ctl);
+        case 128: return launch_rollout_tma_w<A, STRICT, 128>(c, tmap, U, prob, S, ctl);
+        default:  return launch_rollout_tma_w<A, STRICT, 256>(c, tmap, U, prob, S, ctl);
+    }
 }
 
 cudaError_t launch_rollout_tma(const LaunchCtx &c, const CUtensorMap &tmap, const float *U,
@@ -825,6 +922,25 @@ cudaError_t launch_rollout_tma(const LaunchCtx &c, const CUtensorMap &tmap, cons
         return c.strict ? launch_rollout_tma_t<kA, true>(c, tmap, U, prob, S, ctl)
                         : launch_rollout_tma_t<kA, false>(c, tmap, U, prob, S, ctl));
     return cudaSuccess;
+}
+
+template <int A, bool STRICT, int W>
+static cudaError_t configure_rollout_tma_w(int T)
+{
+    return cudaFuncSetAttribute(rollout_tma_kernel<A, STRICT, W>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)rollout_tma_smem_bytes<A>(T, W));
+}
+template <int A>
+static cudaError_t configure_rollout_tma(int T)
+{
+    cudaError_t e;
+    if ((e = configure_rollout_tma_w<A, true, 64>(T)) != cudaSuccess) return e;
+    if ((e = configure_rollout_tma_w<A, true, 128>(T)) != cudaSuccess) return e;
+    if ((e = configure_rollout_tma_w<A, true, 256>(T)) != cudaSuccess) return e;
+    if ((e = configure_rollout_tma_w<A, false, 64>(T)) != cudaSuccess) return e;
+    if ((e = configure_rollout_tma_w<A, false, 128>(T)) != cudaSuccess) return e;
+    return configure_rollout_tma_w<A, false, 256>(T);
 }
 
 int rollout_tma_rows(int A)
@@ -846,14 +962,23 @@ cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev 
     return cudaGetLastError();
 }
 
-cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *wt,
-                           long long *acc)
+cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *src,
+                           long long *acc, bool merge_weights, bool merge_finalize,
+                           const ProblemDev *prob, CtlDev *ctl, float *U, float *U_prev,
+                           float *next_act, unsigned flags)
 {
     const size_t smem = average_smem_bytes(c.rows);
     const int nslab = (int)(c.k_pad / kAvgTileK);
     const int nchunk = (c.rows + kAvgTileR - 1) / kAvgTileR;
-    average_kernel<<<c.avg_grid, kAvgThreads, smem, c.stream>>>(tmap_eps, wt, acc, c.rows, nslab,
-                                                                nchunk);
+    FinalizeArgs fin{U, U_prev, next_act, c.horizon, c.act_dim, flags};
+#define MPPI_AVG_LAUNCH(MW, MF)                                                                  \
+    average_kernel<MW, MF><<<c.avg_grid, kAvgThreads, smem, c.stream>>>(                         \
+        tmap_eps, src, acc, c.rows, nslab, nchunk, (long long)c.k_local, prob, ctl, fin)
+    if (merge_weights && merge_finalize) MPPI_AVG_LAUNCH(true, true);
+    else if (merge_weights)              MPPI_AVG_LAUNCH(true, false);
+    else if (merge_finalize)             MPPI_AVG_LAUNCH(false, true);
+    else                                 MPPI_AVG_LAUNCH(false, false);
+#undef MPPI_AVG_LAUNCH
     return cudaGetLastError();
 }
 
@@ -931,23 +1056,22 @@ static cudaError_t configure_rollout(int smem)
 
 cudaError_t configure_kernels(const LaunchCtx &c)
 {
-    cudaError_t e = cudaFuncSetAttribute(average_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)average_smem_bytes(c.rows));
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
+    const int avg_smem = (int)average_smem_bytes(c.rows);
+    if ((e = cudaFuncSetAttribute(average_kernel<true, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, avg_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(average_kernel<true, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, avg_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(average_kernel<false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, avg_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(average_kernel<false, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, avg_smem)) != cudaSuccess) return e;
     const int fin = (int)(sizeof(float) * (size_t)c.rows);
     if (fin > 48 * 1024) {
         e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
         if (e != cudaSuccess) return e;
     }
-    MPPI_DISPATCH_A(c.act_dim,
-        e = cudaFuncSetAttribute(rollout_tma_kernel<kA, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)rollout_tma_smem_bytes<kA>(c.horizon));
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(rollout_tma_kernel<kA, false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)rollout_tma_smem_bytes<kA>(c.horizon)));
+    MPPI_DISPATCH_A(c.act_dim, e = configure_rollout_tma<kA>(c.horizon));
     if (e != cudaSuccess) return e;
     const int ro = (int)(sizeof(float) * (size_t)c.horizon * 8);
     if (ro > 48 * 1024) {

@@ -32,6 +32,7 @@ struct LaunchCtx {
     int  weights_blocks;   // CTAs of the weights kernel
     int  rollout_spt;      // samples per thread in the rollout kernel (1, 2 or 4)
     bool rollout_tma;      // use the TMA-staged rollout kernel (injected / unfused sampling)
+    int  rollout_tma_width; // its slab width (TMA box inner dim): 64, 128 or 256 samples
     SamplerParams sampler; // Philox round keys of the seed, sigma-derived constants
 };
 
@@ -43,7 +44,8 @@ cudaError_t launch_sample(const LaunchCtx &c, float *eps, const CtlDev *ctl,
 cudaError_t launch_rollout(const LaunchCtx &c, float *eps, const float *U, const ProblemDev *prob,
                            float *S, CtlDev *ctl, bool fused_sampling);
 
-// (2b) the same rollout fed by TMA tiles (tensor map with box {256, rollout_tma_rows(A)})
+// (2b) the same rollout fed by TMA tiles (tensor map with box {rollout_tma_width,
+//      rollout_tma_rows(A)})
 cudaError_t launch_rollout_tma(const LaunchCtx &c, const CUtensorMap &tmap, const float *U,
                                const ProblemDev *prob, float *S, CtlDev *ctl);
 int rollout_tma_rows(int A);
@@ -53,8 +55,13 @@ cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev 
                            const CtlDev *ctl, float *wt, long long *acc);
 
 // (4) acc[r] += sum_{k in cta's tiles} wt[k] * eps[r][k]   (fixed point, r < R)
-cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *wt,
-                           long long *acc);
+//     merge_weights : src = S, the weights (3) are formed inside (acc[R] += eta as well);
+//                     otherwise src = wt from launch_weights
+//     merge_finalize: the last CTA also runs (5) -- single shard only
+cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *src,
+                           long long *acc, bool merge_weights, bool merge_finalize,
+                           const ProblemDev *prob, CtlDev *ctl, float *U, float *U_prev,
+                           float *next_act, unsigned flags);
 
 // (5) U += acc[0..R-1]/acc[R]; shift, next_act, advance step, re-arm acc and min key
 cudaError_t launch_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
