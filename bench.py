@@ -182,15 +182,9 @@ def run_ours(args, name, K, T, A, dt, goal, w):
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
     torch.cuda.set_device(local_rank)
     dist = None
-    comm_id = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        idt = torch.zeros(capi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(m.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        comm_id = bytes(idt.cpu().numpy().tobytes())
 
     def barrier():
         if dist is not None:
@@ -210,8 +204,12 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     k_loc = capi.shard_range(K, rank, world)
     k_loc = k_loc[1] - k_loc[0]
     flags = args.flags if args.flags >= 0 else (capi.FLAG_FUSED_SAMPLING if k_loc >= 400000 else 0)
-    ctl = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=flags, device=local_rank, rank=rank,
-                           world_size=world, comm_id=comm_id)
+    if world > 1:
+        from mppi_gpu_b200.torch_dist import sharded_controller
+        ctl = sharded_controller(K, T, dt, 2 * A, A, comm=args.comm, device=local_rank, seed=0,
+                                 flags=flags)
+    else:
+        ctl = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=flags, device=local_rank)
     x0 = np.zeros(2 * A, np.float32)
     ctl.memcpy_set_data(x0, np.zeros((T, A), np.float32), goal, w)
 
@@ -322,8 +320,7 @@ def run_ours(args, name, K, T, A, dt, goal, w):
         # the canonical 4-part chain (separate sampling kernel) timed beside it, same workload
         ctl.close()
         ctl = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=flags & ~capi.FLAG_FUSED_SAMPLING,
-                               device=local_rank, rank=rank, world_size=world, comm_id=comm_id) \
-            if world == 1 else None
+                               device=local_rank) if world == 1 else None
         if ctl is not None:
             ctl.memcpy_set_data(x0, np.zeros((T, A), np.float32), goal, w)
             for _ in range(3):
@@ -345,8 +342,12 @@ def run_ours(args, name, K, T, A, dt, goal, w):
                                 if k in ("sample", "rollout", "average") else {"ms": v})
                             for k, v in kt4.items()}}
     if world > 1:
-        out["collectives_ms"] = {"allreduce_min_u64": kernels.get("comm_min"),
-                                 "allreduce_sum_i64": kernels.get("comm_sum")}
+        out["collectives_ms"] = {
+            "kind": "NVLink peer mailboxes (direct P2P stores + flags), sum fused with the U update"
+                    if args.comm == "p2p" else "ncclAllReduce inside the CUDA graph",
+            "min_u64": kernels.get("comm_min"),
+            "sum_i64" + ("+finalize" if args.comm == "p2p" else ""): kernels.get("comm_sum")}
+        out["config"]["comm"] = args.comm
 
     # ---- CPU baseline beside it (rank 0, N=1 only): 1 core, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -383,6 +384,8 @@ def main():
     ap.add_argument("--flags", type=int, default=-1,
                     help="MPPI_FLAG_* bits; default: fused sampling (32) when >= 4e5 samples/GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="K-shard exchange for --gpus > 1: NVLink peer mailboxes or NCCL")
     args = ap.parse_args()
     K, T, A, dt, goal, w = WORKLOADS[args.workload]
     if args.impl == "reference":

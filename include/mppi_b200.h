@@ -67,6 +67,10 @@ extern "C" {
 #define MPPI_COMM_NONE  0   /* single shard                                          */
 #define MPPI_COMM_NCCL  1   /* ncclAllReduce(min) for beta, ncclAllReduce(sum) for the
                                weighted-noise partials and eta                       */
+#define MPPI_COMM_P2P   2   /* the same two exchanges as direct stores into peer mailboxes
+                               over NVLink (CUDA IPC), fused with the U update: no NCCL
+                               kernel on the step's critical path                    */
+#define MPPI_P2P_HANDLE_BYTES 64
 
 typedef struct mppi_handle mppi_handle;
 
@@ -190,8 +194,14 @@ int mppi_get_kernel_times(mppi_handle *h, double *ms_sum, int64_t *launches);
 int mppi_get_launch_count(mppi_handle *h, int64_t *launches);
 const char *mppi_kernel_name(int kernel_id);
 
-/* multi-shard setup: rank 0 creates the id, every rank passes it in mppi_params */
+/* multi-shard setup, MPPI_COMM_NCCL: rank 0 creates the id, every rank passes it in
+ * mppi_params */
 int mppi_comm_unique_id(uint8_t id[MPPI_COMM_ID_BYTES]);
+/* multi-shard setup, MPPI_COMM_P2P (one process per GPU of one NVLink domain): after
+ * mppi_create every rank exports the IPC handle of its mailbox, the host all-gathers the
+ * world_size x 64 bytes (rank order) and every rank connects. */
+int mppi_comm_p2p_handle(mppi_handle *h, uint8_t out[MPPI_P2P_HANDLE_BYTES]);
+int mppi_comm_p2p_connect(mppi_handle *h, const uint8_t *handles);
 
 const char *mppi_last_error(void);
 int mppi_abi_version(void);

@@ -28,7 +28,8 @@ FLAG_NO_GRAPH = 1 << 4
 FLAG_FUSED_SAMPLING = 1 << 5
 FLAG_SPLIT_KERNELS = 1 << 6
 
-COMM_NONE, COMM_NCCL = 0, 1
+COMM_NONE, COMM_NCCL, COMM_P2P = 0, 1, 2
+P2P_HANDLE_BYTES = 64
 
 K_SAMPLE, K_ROLLOUT, K_COMM_MIN, K_WEIGHTS, K_AVERAGE, K_COMM_SUM, K_FINALIZE, K_COUNT = range(8)
 
@@ -39,7 +40,8 @@ EXPORTS = [
     "mppi_get_info", "mppi_get_step_info", "mppi_set_noise", "mppi_set_noise_mode",
     "mppi_sample_only", "mppi_shard_range", "mppi_local_samples", "mppi_timer_start", "mppi_timer_stop",
     "mppi_set_profiling", "mppi_get_kernel_times", "mppi_get_launch_count", "mppi_kernel_name",
-    "mppi_comm_unique_id", "mppi_last_error", "mppi_abi_version",
+    "mppi_comm_unique_id", "mppi_comm_p2p_handle", "mppi_comm_p2p_connect", "mppi_last_error",
+    "mppi_abi_version",
 ]
 
 
@@ -121,6 +123,8 @@ def load():
     L.mppi_get_kernel_times.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.mppi_get_launch_count.argtypes = [H, C.POINTER(C.c_int64)]
     L.mppi_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    L.mppi_comm_p2p_handle.argtypes = [H, C.POINTER(C.c_uint8)]
+    L.mppi_comm_p2p_connect.argtypes = [H, C.POINTER(C.c_uint8)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("mppi_last_error", "mppi_kernel_name"):

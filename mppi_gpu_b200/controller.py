@@ -20,7 +20,7 @@ class PointMassModel:
 
     def __init__(self, nb_sim, steps, dt, state_dim, act_dim, verbose=False, *, lam=1.0,
                  sigma=0.025, inv_sigma=1.0, init_act=0.0, max_act=1.0, seed=0, flags=0,
-                 device=0, rank=0, world_size=1, comm_id=None):
+                 device=0, rank=0, world_size=1, comm_id=None, comm=None):
         self._lib = capi.load()
         p = capi.MppiParams()
         capi.check(self._lib.mppi_params_default(C.byref(p)))
@@ -36,10 +36,11 @@ class PointMassModel:
         p.seed, p.flags, p.device = int(seed), int(flags), int(device)
         p.rank, p.world_size = int(rank), int(world_size)
         if world_size > 1:
-            p.comm = capi.COMM_NCCL
-            assert comm_id is not None and len(comm_id) == capi.COMM_ID_BYTES
-            for i, b in enumerate(bytes(comm_id)):
-                p.comm_id[i] = b
+            p.comm = capi.COMM_NCCL if comm is None else int(comm)
+            if p.comm == capi.COMM_NCCL:
+                assert comm_id is not None and len(comm_id) == capi.COMM_ID_BYTES
+                for i, b in enumerate(bytes(comm_id)):
+                    p.comm_id[i] = b
         self.params = p
         self._h = C.c_void_p()
         capi.check(self._lib.mppi_create(C.byref(p), C.byref(self._h)))
@@ -147,6 +148,16 @@ class PointMassModel:
         n = C.c_int64()
         capi.check(self._lib.mppi_get_launch_count(self._h, C.byref(n)))
         return int(n.value)
+
+    def p2p_handle(self) -> bytes:
+        buf = (C.c_uint8 * capi.P2P_HANDLE_BYTES)()
+        capi.check(self._lib.mppi_comm_p2p_handle(self._h, buf))
+        return bytes(buf)
+
+    def p2p_connect(self, handles: bytes):
+        assert len(handles) == capi.P2P_HANDLE_BYTES * self.params.world_size
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        capi.check(self._lib.mppi_comm_p2p_connect(self._h, buf))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

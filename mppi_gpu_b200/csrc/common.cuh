@@ -39,6 +39,8 @@ struct CtlDev {
     unsigned long long last_key;  // min_key of the last finished step (for get_step_info)
     float eta;                    // normaliser of the last finished step
     unsigned int done;            // CTA ticket counter of the merged average+finalize kernel
+    unsigned int comm_error;      // set when a peer-mailbox wait timed out
+    unsigned int pad_;
 };
 
 constexpr unsigned long long kMinKeyInit = ~0ull;
@@ -181,6 +183,39 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap)
 {
     asm volatile("prefetch.tensormap [%0];" :: "l"(tmap) : "memory");
 }
+
+// ---------------------------------------------------------------------------------
+// system-scope accesses for the peer-mailbox exchange over NVLink (multi-GPU)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 #endif  // __CUDACC__
+
+// Peer mailbox of one rank: slot s is written only by rank s (over NVLink for s != self).
+//   [0] key_seq  [1] key  [2] acc_seq  [3] reserved  [4 ...] acc[R+1]
+constexpr int kMailboxHeaderWords = 4;
+constexpr int kMaxWorld = 16;
+inline size_t mailbox_slot_words(int rows)
+{
+    return (size_t)((kMailboxHeaderWords + rows + 1 + 15) / 16 * 16);     // 128-byte multiple
+}
 
 }  // namespace mppi

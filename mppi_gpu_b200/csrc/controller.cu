@@ -70,6 +70,9 @@ struct mppi_handle {
     CUtensorMap tmap_ro{};     // TMA rollout: box {256, TT*A}
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // [0] sampling, [1] injected noise
     NcclComm comm;
+    unsigned long long *d_mailbox = nullptr;              // MPPI_COMM_P2P: this rank's mailbox
+    unsigned long long *peer_mb[kMaxWorld] = {};          // every rank's mailbox mapped here
+    bool p2p_connected = false;
 
     bool problem_set = false;
     bool injected = false;
@@ -86,6 +89,7 @@ struct mppi_handle {
 namespace {
 
 bool multi(const mppi_handle *h) { return h->p.world_size > 1; }
+bool p2p(const mppi_handle *h) { return multi(h) && h->p.comm == MPPI_COMM_P2P; }
 bool fused(const mppi_handle *h) { return (h->p.flags & MPPI_FLAG_FUSED_SAMPLING) != 0; }
 
 int encode_tmap(mppi_handle *h, CUtensorMap *out, int box_cols, int box_rows)
@@ -129,7 +133,9 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
     else
         CK(launch_rollout(c, h->d_eps, h->d_U, h->d_prob, h->d_S, h->d_ctl, sample && fused(h)));
     CK(mark());
-    if (multi(h)) {
+    if (p2p(h)) {
+        CK(launch_xchg_min(c, h->d_ctl, h->peer_mb, h->p.rank, h->p.world_size));
+    } else if (multi(h)) {
         if (!h->comm.allreduce_min_u64(&h->d_ctl->min_key, 1, c.stream, err))
             return fail(MPPI_ERR_COMM, "%s", err.c_str());
     }
@@ -141,15 +147,20 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
     CK(launch_average(c, h->tmap, split ? h->d_wt : h->d_S, h->d_acc, !split, merge_fin, h->d_prob,
                       h->d_ctl, h->d_U, h->d_Uprev, h->d_next, h->p.flags));
     CK(mark());
-    if (multi(h)) {
+    if (p2p(h)) {
+        // exchange + integer sum + U update in one kernel over peer memory
+        CK(launch_xchg_sum_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
+                                    h->p.flags, h->peer_mb, h->p.rank, h->p.world_size));
+    } else if (multi(h)) {
         if (!h->comm.allreduce_sum_i64(h->d_acc, (size_t)h->R + 1, c.stream, err))
             return fail(MPPI_ERR_COMM, "%s", err.c_str());
     }
     CK(mark());
-    if (!merge_fin)
+    if (!merge_fin && !p2p(h))
         CK(launch_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
                            h->p.flags));
-    CK(cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * h->p.act_dim, cudaMemcpyDeviceToHost,
+    // next action (A floats) + the exchange error flag at [kMaxAct]
+    CK(cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * (kMaxAct + 1), cudaMemcpyDeviceToHost,
                        c.stream));
     CK(mark());
     return MPPI_OK;
@@ -159,8 +170,9 @@ int kernels_per_step(const mppi_handle *h, bool sample)
 {
     int n = 2;                                  // rollout, average(+weights,+finalize)
     if (sample && !fused(h)) n += 1;            // sampling
-    if (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) n += 2;      // separate weights, finalize
-    else if (multi(h)) n += 1;                  // finalize after the all-reduce
+    if (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) n += 1;      // separate weights kernel
+    if (p2p(h)) n += 2;                         // xchg_min, xchg_sum+finalize
+    else if (multi(h) || (h->p.flags & MPPI_FLAG_SPLIT_KERNELS)) n += 1;   // finalize kernel
     return n;
 }
 
@@ -234,11 +246,46 @@ int mppi_comm_unique_id(uint8_t id[MPPI_COMM_ID_BYTES])
     return MPPI_OK;
 }
 
+int mppi_comm_p2p_handle(mppi_handle *h, uint8_t out[MPPI_P2P_HANDLE_BYTES])
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!p2p(h) || !out) return fail(MPPI_ERR_INVALID, "handle was not created with MPPI_COMM_P2P");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MPPI_P2P_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t ipc;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaIpcGetMemHandle(&ipc, h->d_mailbox));
+    memcpy(out, &ipc, sizeof ipc);
+    return MPPI_OK;
+}
+
+int mppi_comm_p2p_connect(mppi_handle *h, const uint8_t *handles)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!p2p(h) || !handles) return fail(MPPI_ERR_INVALID, "handle was not created with MPPI_COMM_P2P");
+    for (int r = 0; r < h->p.world_size; ++r) {
+        if (r == h->p.rank) continue;
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, handles + (size_t)r * MPPI_P2P_HANDLE_BYTES, sizeof ipc);
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return fail(MPPI_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
+        h->peer_mb[r] = static_cast<unsigned long long *>(ptr);
+    }
+    h->p2p_connected = true;
+    return MPPI_OK;
+}
+
 int mppi_destroy(mppi_handle *h)
 {
     if (!h) return MPPI_OK;
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < kMaxWorld; ++r)
+        if (h->peer_mb[r] && h->peer_mb[r] != h->d_mailbox) cudaIpcCloseMemHandle(h->peer_mb[r]);
+    cudaFree(h->d_mailbox);
     for (auto &g : h->graph_exec) if (g) cudaGraphExecDestroy(g);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->t0) cudaEventDestroy(h->t0);
@@ -273,8 +320,10 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     if (!(p.lambda > 0.0f)) return fail(MPPI_ERR_INVALID, "lambda must be > 0");
     if (p.world_size < 1 || p.rank < 0 || p.rank >= p.world_size)
         return fail(MPPI_ERR_INVALID, "rank %d / world_size %d invalid", p.rank, p.world_size);
-    if (p.world_size > 1 && p.comm != MPPI_COMM_NCCL)
-        return fail(MPPI_ERR_INVALID, "world_size > 1 needs comm = MPPI_COMM_NCCL");
+    if (p.world_size > 1 && p.comm != MPPI_COMM_NCCL && p.comm != MPPI_COMM_P2P)
+        return fail(MPPI_ERR_INVALID, "world_size > 1 needs comm = MPPI_COMM_NCCL or MPPI_COMM_P2P");
+    if (p.world_size > kMaxWorld)
+        return fail(MPPI_ERR_INVALID, "world_size %d > %d", p.world_size, kMaxWorld);
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -359,11 +408,18 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     CKH(cudaMalloc(&h->d_acc, sizeof(long long) * ((size_t)h->R + 1)));
     CKH(cudaMalloc(&h->d_U, sizeof(float) * (size_t)h->R));
     CKH(cudaMalloc(&h->d_Uprev, sizeof(float) * (size_t)h->R));
-    CKH(cudaMalloc(&h->d_next, sizeof(float) * kMaxAct));
+    CKH(cudaMalloc(&h->d_next, sizeof(float) * 2 * kMaxAct));
+    CKH(cudaMemsetAsync(h->d_next, 0, sizeof(float) * 2 * kMaxAct, h->stream));
+    if (p.world_size > 1 && p.comm == MPPI_COMM_P2P) {
+        const size_t mb_bytes = sizeof(unsigned long long) * mailbox_slot_words(h->R) * p.world_size;
+        CKH(cudaMalloc(&h->d_mailbox, mb_bytes));
+        CKH(cudaMemsetAsync(h->d_mailbox, 0, mb_bytes, h->stream));
+        h->peer_mb[p.rank] = h->d_mailbox;
+    }
     CKH(cudaMalloc(&h->d_prob, sizeof(ProblemDev)));
     CKH(cudaMalloc(&h->d_ctl, sizeof(CtlDev)));
     CKH(cudaMallocHost(&h->h_stage, sizeof(float) * kStageSlots * 2 * kMaxAct));
-    CKH(cudaMallocHost(&h->h_next, sizeof(float) * kMaxAct));
+    CKH(cudaMallocHost(&h->h_next, sizeof(float) * 2 * kMaxAct));
     // eps zeroed like the reference's cudaMemset(_e, 0) (src/point_mass.cu:69): keeps the
     // pad columns finite and defines injected-noise mode before the first mppi_set_noise.
     CKH(cudaMemsetAsync(h->d_eps, 0, eps_bytes, h->stream));
@@ -399,7 +455,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     if ((rc = encode_tmap(h, &h->tmap, kAvgTileK, kAvgTileR)) != MPPI_OK) { mppi_destroy(h); return rc; }
     if ((rc = encode_tmap(h, &h->tmap_ro, c.rollout_tma_width, rollout_tma_rows(p.act_dim))) != MPPI_OK) { mppi_destroy(h); return rc; }
 
-    if (multi(h)) {
+    if (multi(h) && p.comm == MPPI_COMM_NCCL) {
         std::string err;
         if (!h->comm.init(p.rank, p.world_size, p.comm_id, err)) {
             rc = fail(MPPI_ERR_COMM, "%s", err.c_str());
@@ -485,6 +541,8 @@ int mppi_step_enqueue(mppi_handle *h)
     int rc = check_handle(h);
     if (rc) return rc;
     if (!h->problem_set) return fail(MPPI_ERR_STATE, "mppi_step before mppi_set_problem");
+    if (p2p(h) && !h->p2p_connected)
+        return fail(MPPI_ERR_STATE, "mppi_step before mppi_comm_p2p_connect");
     const bool sample = !h->injected;
     const int which = sample ? 0 : 1;
     if (h->profiling || (h->p.flags & MPPI_FLAG_NO_GRAPH)) {
@@ -501,7 +559,7 @@ int mppi_step_enqueue(mppi_handle *h)
                 const bool ran = (i == MPPI_K_SAMPLE) ? (sample && !fused(h))
                                : (i == MPPI_K_COMM_MIN || i == MPPI_K_COMM_SUM) ? multi(h)
                                : (i == MPPI_K_WEIGHTS) ? split
-                               : (i == MPPI_K_FINALIZE) ? (split || multi(h)) : true;
+                               : (i == MPPI_K_FINALIZE) ? ((split || multi(h)) && !p2p(h)) : true;
                 if (ran) { h->ms_sum[i] += ms; h->launches[i] += 1; }
             }
         }
@@ -522,6 +580,8 @@ int mppi_step_wait(mppi_handle *h, float *next_act)
     h->pending = false;
     if (next_act)
         for (int a = 0; a < h->p.act_dim; ++a) next_act[a] = h->h_next[a];
+    if (h->h_next[kMaxAct] != 0.0f)
+        return fail(MPPI_ERR_COMM, "peer-mailbox exchange timed out (a rank did not arrive)");
     return MPPI_OK;
 }
 

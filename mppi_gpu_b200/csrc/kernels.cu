@@ -529,6 +529,7 @@ __device__ __forceinline__ void finalize_body(long long *acc, float *__restrict_
     }
     if (threadIdx.x < A) next_act[threadIdx.x] = s_u[threadIdx.x];
     if (threadIdx.x == 0) {
+        next_act[kMaxAct] = ctl->comm_error ? 1.0f : 0.0f;    // read by the host with next_act
         acc[R] = 0;
         ctl->eta = eta;
         ctl->last_key = ctl->min_key;
@@ -729,6 +730,90 @@ finalize_kernel(long long *__restrict__ acc, float *__restrict__ U, float *__res
 }
 
 // =================================================================================
+// K-shard exchange over NVLink peer memory (MPPI_COMM_P2P): every rank owns a mailbox with
+// one slot per sender; a sender stores its contribution straight into every peer's mailbox
+// (st.relaxed.sys), fences, then publishes a sequence number (st.release.sys); the owner
+// polls its own memory (ld.acquire.sys).  Sequence = control step + 1, so nothing is ever
+// reset and a stale flag can never match.  Replaces the two latency-bound NCCL all-reduces
+// (one kernel launch + ~20-30 us each at 8 ranks) with two single-CTA kernels, the second of
+// which also performs the U update.  A bounded spin (about a second) turns a dead peer into
+// an error code instead of a hang.
+// =================================================================================
+struct PeerTable {
+    unsigned long long *mb[kMaxWorld];     // mailbox base of every rank, as mapped in THIS process
+};
+
+__device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigned long long seq)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(flag) != seq) {
+        if (clock64() - t0 > 4000000000ll) return false;      // ~2 s at 2 GHz
+        __nanosleep(64);
+    }
+    return true;
+}
+
+// (3a) beta = min over all shards of the packed (cost, index) key
+__global__ void __launch_bounds__(32)
+xchg_min_kernel(CtlDev *__restrict__ ctl, const __grid_constant__ PeerTable peers, int rank,
+                int world, size_t slot_words)
+{
+    const int lane = threadIdx.x;
+    const unsigned long long seq = ctl->step + 1;
+    const unsigned long long mine = ctl->min_key;
+    unsigned long long key = kMinKeyInit;
+    if (lane < world) {
+        unsigned long long *slot = peers.mb[lane] + (size_t)rank * slot_words;   // my slot at peer
+        st_relaxed_sys_u64(slot + 1, mine);
+        __threadfence_system();
+        st_release_sys_u64(slot + 0, seq);
+        const unsigned long long *in = peers.mb[rank] + (size_t)lane * slot_words;  // lane's slot here
+        if (wait_seq(in + 0, seq)) key = ld_relaxed_sys_u64(in + 1);
+        else atomicExch(&ctl->comm_error, 1u);
+    }
+    key = warp_min_u64(key);
+    if (lane == 0) ctl->min_key = key;
+}
+
+// (5') all-reduce(sum) of the fixed-point accumulators through the mailboxes, then finalize
+__global__ void __launch_bounds__(256)
+xchg_sum_finalize_kernel(long long *__restrict__ acc, float *__restrict__ U,
+                         float *__restrict__ U_prev, const ProblemDev *__restrict__ prob,
+                         CtlDev *__restrict__ ctl, float *__restrict__ next_act, int T, int A,
+                         unsigned flags, const __grid_constant__ PeerTable peers, int rank, int world,
+                         size_t slot_words)
+{
+    extern __shared__ float s_u[];
+    const int R = T * A;
+    const unsigned long long seq = ctl->step + 1;
+    // push my accumulators into every peer's mailbox (including my own)
+    for (int r = 0; r < world; ++r) {
+        unsigned long long *slot = peers.mb[r] + (size_t)rank * slot_words + kMailboxHeaderWords;
+        for (int i = threadIdx.x; i <= R; i += blockDim.x)
+            st_relaxed_sys_u64(slot + i, (unsigned long long)acc[i]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        st_release_sys_u64(peers.mb[threadIdx.x] + (size_t)rank * slot_words + 2, seq);
+        const unsigned long long *in = peers.mb[rank] + (size_t)threadIdx.x * slot_words;
+        if (!wait_seq(in + 2, seq)) atomicExch(&ctl->comm_error, 1u);
+    }
+    __syncthreads();
+    // integer sum in rank order (exact: any order gives the same bits)
+    for (int i = threadIdx.x; i <= R; i += blockDim.x) {
+        long long sum = 0;
+        for (int r = 0; r < world; ++r)
+            sum += (long long)ld_relaxed_sys_u64(peers.mb[rank] + (size_t)r * slot_words +
+                                                 kMailboxHeaderWords + i);
+        acc[i] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    finalize_body(acc, U, U_prev, prob, ctl, next_act, T, A, flags, s_u);
+}
+
+// =================================================================================
 // layout conversion (parity taps): reference [K][R]  <->  internal [R][k_pad]
 // =================================================================================
 __global__ void __launch_bounds__(256)
@@ -827,6 +912,7 @@ __global__ void clear_ctl_kernel(CtlDev *ctl)
     ctl->step = 0;
     ctl->eta = 0.0f;
     ctl->done = 0;
+    ctl->comm_error = 0;
 }
 
 // =================================================================================
@@ -991,6 +1077,29 @@ cudaError_t launch_finalize(const LaunchCtx &c, long long *acc, float *U, float 
     return cudaGetLastError();
 }
 
+cudaError_t launch_xchg_min(const LaunchCtx &c, CtlDev *ctl, unsigned long long *const *peer_mb,
+                            int rank, int world)
+{
+    PeerTable pt{};
+    for (int r = 0; r < world; ++r) pt.mb[r] = peer_mb[r];
+    xchg_min_kernel<<<1, 32, 0, c.stream>>>(ctl, pt, rank, world, mailbox_slot_words(c.rows));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xchg_sum_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
+                                     const ProblemDev *prob, CtlDev *ctl, float *next_act,
+                                     unsigned flags, unsigned long long *const *peer_mb, int rank,
+                                     int world)
+{
+    PeerTable pt{};
+    for (int r = 0; r < world; ++r) pt.mb[r] = peer_mb[r];
+    const size_t smem = sizeof(float) * (size_t)c.rows;
+    xchg_sum_finalize_kernel<<<1, 256, smem, c.stream>>>(acc, U, U_prev, prob, ctl, next_act,
+                                                         c.horizon, c.act_dim, flags, pt, rank,
+                                                         world, mailbox_slot_words(c.rows));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_to_internal(const LaunchCtx &c, const float *e_ref, float *eps)
 {
     dim3 grid((unsigned)((c.k_local + 31) / 32), (unsigned)((c.rows + 31) / 32));
@@ -1069,6 +1178,9 @@ cudaError_t configure_kernels(const LaunchCtx &c)
     const int fin = (int)(sizeof(float) * (size_t)c.rows);
     if (fin > 48 * 1024) {
         e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(xchg_sum_finalize_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
         if (e != cudaSuccess) return e;
     }
     MPPI_DISPATCH_A(c.act_dim, e = configure_rollout_tma<kA>(c.horizon));

@@ -67,6 +67,15 @@ cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, cons
 cudaError_t launch_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
                             const ProblemDev *prob, CtlDev *ctl, float *next_act, unsigned flags);
 
+// K-shard exchange over NVLink peer mailboxes (MPPI_COMM_P2P); peer_mb[r] = mailbox of rank r
+// as mapped in this process (cudaIpcOpenMemHandle), peer_mb[rank] = the local one
+cudaError_t launch_xchg_min(const LaunchCtx &c, CtlDev *ctl, unsigned long long *const *peer_mb,
+                            int rank, int world);
+cudaError_t launch_xchg_sum_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
+                                     const ProblemDev *prob, CtlDev *ctl, float *next_act,
+                                     unsigned flags, unsigned long long *const *peer_mb, int rank,
+                                     int world);
+
 // layout conversion between the reference's [K][T*A] and the internal K-minor [T*A][k_pad]
 cudaError_t launch_to_internal(const LaunchCtx &c, const float *e_ref, float *eps);
 cudaError_t launch_to_reference(const LaunchCtx &c, const float *eps, float *e_ref);

@@ -4,7 +4,8 @@ mode "gloo": CPU-only check of the K-shard exchange logic that the C ABI impleme
   GPU: shard ranges from mppi_shard_range, per-shard oracle rollouts, all-reduce(min) of the
   packed (ordered cost, global index) key, all-reduce(sum) of the 2^30 fixed-point
   accumulators; the result must equal the single-shard oracle step.
-mode "nccl": the real thing on GPUs -- every rank owns one shard of one controller.
+mode "nccl" / "p2p": the real thing on GPUs -- every rank owns one shard of one controller,
+  exchanging through NCCL all-reduces or through the NVLink peer mailboxes.
 """
 import os
 import sys
@@ -69,25 +70,19 @@ def gloo_mode():
     dist.destroy_process_group()
 
 
-def nccl_mode():
-    import mppi_gpu_b200 as m
+def gpu_mode(comm):
     from mppi_gpu_b200 import capi
+    from mppi_gpu_b200.torch_dist import sharded_controller
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    idt = torch.zeros(capi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(m.comm_unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    comm_id = bytes(idt.cpu().numpy().tobytes())
 
     K, T, A, lam = 20003, 40, 3, 5.0
     cfg = REF_CFG[A]
     x0, U, _ = make_inputs(K, T, A, seed=3)
-    ctl = m.PointMassModel(K, T, 0.1, 2 * A, A, lam=lam, seed=11, device=local, rank=rank,
-                           world_size=world, comm_id=comm_id)
+    ctl = sharded_controller(K, T, 0.1, 2 * A, A, comm=comm, device=local, lam=lam, seed=11)
     k0, k1 = capi.shard_range(K, rank, world)
     assert (ctl.k_offset, ctl.k_local) == (k0, k1 - k0)
     ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
@@ -130,7 +125,7 @@ def nccl_mode():
     ctl.close()
     dist.barrier()
     if rank == 0:
-        print("NCCL_OK")
+        print(comm.upper() + "_OK")
     dist.destroy_process_group()
 
 
@@ -139,7 +134,10 @@ if __name__ == "__main__":
     import traceback
     signal.alarm(150)                 # never outlive the test: a dead peer must not hang us
     try:
-        {"gloo": gloo_mode, "nccl": nccl_mode}[sys.argv[1]]()
+        if sys.argv[1] == "gloo":
+            gloo_mode()
+        else:
+            gpu_mode(sys.argv[1])
     except BaseException:
         traceback.print_exc()
         sys.stderr.flush()

@@ -28,10 +28,11 @@ def test_k_shard_exchange_logic_gloo_world3():
 
 
 @pytest.mark.gpu
-def test_k_sharded_controller_nccl():
+@pytest.mark.parametrize("comm", ["nccl", "p2p"])
+def test_k_sharded_controller(comm):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
-    r = _launch("nccl", min(n, 4), 29543)
-    assert r.returncode == 0 and "NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    r = _launch(comm, min(n, 4), 29543 + (comm == "p2p"))
+    assert r.returncode == 0 and comm.upper() + "_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
