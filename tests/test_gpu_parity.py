@@ -323,6 +323,7 @@ def test_profiling_mode_reports_every_kernel(M):
         ctl = M.PointMassModel(K, T, 0.1, 4, 2, flags=flags, seed=3)
         ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
         ctl.get_act()
+        results[flags] = (ctl.get_u(), ctl.get_inf(want_e=False)["cost"], ctl.step_info())
         ctl.set_profiling(True)
         for _ in range(3):
             ctl.get_act()
@@ -334,10 +335,9 @@ def test_profiling_mode_reports_every_kernel(M):
             else:
                 assert n == 0, (flags, name)
         assert ctl.launch_count() == 4 * per_step
-        results[flags] = (ctl.get_u(), ctl.get_inf(want_e=False)["cost"], ctl.step_info())
         ctl.close()
-    # merged, split and fused chains are the same computation: identical costs, beta and
-    # argmin; U agrees to rounding (eta partials are grouped differently before they enter
+    # merged, split and fused chains are the same computation (compared after the first
+    # step, from the same U): identical costs, beta and argmin; U agrees to rounding (eta partials are grouped differently before they enter
     # the fixed-point accumulator)
     ref = results[0]
     for flags, (u, cost, info) in results.items():
