@@ -112,6 +112,100 @@ struct PointMass {
     }
 };
 
+// ---------------------------------------------------------------------------------
+// Packed FP32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2).  One instruction performs the
+// IEEE operation on two independent float lanes, so two samples advance per issue slot with
+// exactly the bits the scalar code produces.  The FMA pipe rate per FLOP is unchanged
+// (measured: 123 vs 119 FMA/clk/SM, tools/ubench/ffma2.cu); what is saved is issue slots,
+// which is what the rollout -- and above all the fused sample+rollout kernel, whose Philox
+// integer and MUFU work competes for the same issue ports -- is bound by.
+// ---------------------------------------------------------------------------------
+struct f2 { unsigned long long r; };
+__device__ __forceinline__ f2 mk2(float lo, float hi)
+{
+    f2 o; asm("mov.b64 %0, {%1,%2};" : "=l"(o.r) : "f"(lo), "f"(hi)); return o;
+}
+__device__ __forceinline__ void un2(f2 a, float &lo, float &hi)
+{
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.r));
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+    f2 o; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(o.r) : "l"(a.r), "l"(b.r)); return o;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b)
+{
+    f2 o; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(o.r) : "l"(a.r), "l"(b.r)); return o;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b)
+{
+    f2 o; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(o.r) : "l"(a.r), "l"(b.r)); return o;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
+{
+    f2 o; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(o.r) : "l"(a.r), "l"(b.r), "l"(c.r)); return o;
+}
+// A product whose result feeds an ADD.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 even though both carry an explicit .rn (it honours .rn for the scalar forms only; seen
+// in the SASS, and in the parity tests as 1-2 ulp cost differences).  fma(a, b, +0) rounds
+// exactly like the product and cannot be merged with the following add; it costs the same
+// issue slot.  Only the sign of a zero product can differ, which no cost term can see.
+__device__ __forceinline__ f2 mulp2(f2 a, f2 b)
+{
+    f2 z; z.r = 0ull;
+    return fma2(a, b, z);
+}
+
+// PointMass on a PAIR of samples: same operations, same order, two lanes.
+template <int A, bool STRICT>
+struct PointMass2 {
+    f2 dt, b0, b1, lambda;
+    f2 goal[2 * A], w[2 * A];
+
+    __device__ __forceinline__ void load(const ProblemDev *__restrict__ p)
+    {
+        dt = mk2(p->g[1], p->g[1]); b0 = mk2(p->b[0], p->b[0]); b1 = mk2(p->b[1], p->b[1]);
+        lambda = mk2(p->lambda, p->lambda);
+#pragma unroll
+        for (int i = 0; i < 2 * A; ++i) {
+            goal[i] = mk2(p->goal[i], p->goal[i]);
+            w[i] = mk2(p->w[i], p->w[i]);
+        }
+    }
+    __device__ __forceinline__ f2 state_cost(const f2 (&x)[2 * A], f2 res) const
+    {
+#pragma unroll
+        for (int i = 0; i < 2 * A; ++i) {
+            const f2 d = sub2(x[i], goal[i]);
+            if (STRICT) res = add2(res, mulp2(mul2(d, w[i]), d));
+            else        res = fma2(mul2(d, w[i]), d, res);
+        }
+        return res;
+    }
+    __device__ __forceinline__ void step(f2 (&x)[2 * A], f2 &c, const f2 (&u)[A], const f2 (&ui)[A],
+                                         const f2 (&e)[A]) const
+    {
+        f2 res = mk2(0.0f, 0.0f);
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            const f2 ue = add2(u[i], e[i]);
+            const f2 p = x[i], v = x[i + A];
+            if (STRICT) {
+                x[i]     = add2(add2(p, mulp2(dt, v)), mulp2(b0, ue));
+                x[i + A] = add2(v, mulp2(b1, ue));
+                res = add2(res, mulp2(ui[i], e[i]));
+            } else {
+                x[i]     = fma2(b0, ue, add2(p, mulp2(dt, v)));
+                x[i + A] = fma2(b1, ue, v);
+                res = fma2(ui[i], e[i], res);
+            }
+        }
+        res = STRICT ? mulp2(res, lambda) : mul2(res, lambda);   // feeds an add when STRICT
+        res = state_cost(x, res);
+        c = add2(c, res);
+    }
+};
+
 // vector load of SPT consecutive floats through the non-coherent, no-L1-allocate path
 template <int SPT> struct EpsVec;
 template <> struct EpsVec<1> {
@@ -137,6 +231,22 @@ template <> struct EpsVec<4> {
 // U staging in shared memory: per time step one 16-byte aligned record
 // {u_0, u_0*inv_s_0, u_1, u_1*inv_s_1, ...} so a thread fetches a whole step with one or two
 // LDS.128 (broadcast) instead of 2A scalar loads.
+// Packed variant for the FP32x2 path: {u_a, u_a, u_a*inv_s_a, u_a*inv_s_a} per action dim, so
+// one LDS.128 yields the two lane-duplicated operands directly.
+template <int A> struct UStage2 {
+    static constexpr int kStride = 4 * A;                    // floats per step
+    static __device__ __forceinline__ void fetch(const float *s, int t, f2 (&u)[A], f2 (&ui)[A])
+    {
+        const float4 *p = reinterpret_cast<const float4 *>(s + (size_t)t * kStride);
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const float4 v = p[a];
+            u[a] = mk2(v.x, v.y);
+            ui[a] = mk2(v.z, v.w);
+        }
+    }
+};
+
 template <int A> struct UStage {
     static constexpr int kStride = (2 * A + 3) / 4 * 4;     // floats per step
     static __device__ __forceinline__ void fetch(const float *s, int t, float (&u)[A], float (&ui)[A])
@@ -156,6 +266,7 @@ template <int A> struct UStage {
 // One thread integrates SPT consecutive samples.  eps is consumed in chunks of CH time
 // steps through a register double buffer: the loads of chunk c+1 are issued before the
 // arithmetic of chunk c, so every thread keeps CH*A vector loads (96 B for A=3) in flight.
+// SPT >= 2: the samples advance in pairs on the packed FP32x2 path (PointMass2).
 template <int A, bool STRICT, bool FUSED, int SPT>
 __global__ void __launch_bounds__(256, (SPT == 1 ? 3 : 2))
 rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
@@ -165,15 +276,23 @@ rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
 {
     static_assert(!FUSED || SPT == 4, "fused sampling works on Philox quads");
     constexpr int CH = 8 / SPT;
-    constexpr int UST = UStage<A>::kStride;
+    constexpr bool PACKED = SPT >= 2;
+    constexpr int NP = PACKED ? SPT / 2 : 1;                  // sample pairs per thread
+    constexpr int UST = PACKED ? UStage2<A>::kStride : UStage<A>::kStride;
     extern __shared__ __align__(16) float smem_f[];          // [T][UST]
     __shared__ unsigned long long s_key[8];
 
     for (int i = threadIdx.x; i < T * A; i += blockDim.x) {
         const float u = U[i];
+        const float ui = __fmul_rn(u, prob->inv_s[i % A]);   // src/cost.cu:46
         const int t = i / A, a = i - t * A;
-        smem_f[t * UST + 2 * a]     = u;
-        smem_f[t * UST + 2 * a + 1] = __fmul_rn(u, prob->inv_s[a]);   // src/cost.cu:46
+        if (PACKED) {
+            float4 *rec = reinterpret_cast<float4 *>(smem_f + (size_t)t * UST) + a;
+            *rec = make_float4(u, u, ui, ui);
+        } else {
+            smem_f[t * UST + 2 * a]     = u;
+            smem_f[t * UST + 2 * a + 1] = ui;
+        }
     }
     __syncthreads();
 
@@ -181,28 +300,44 @@ rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
     unsigned long long key = kMinKeyInit;
 
     if (SPT * g < ld) {
-        PointMass<A, STRICT> m;
-        m.load(prob);
-        float x[SPT][2 * A];
-        float c[SPT];
+        // ---- per-thread state: scalar (SPT == 1) or packed pairs
+        PointMass<A, STRICT> m1;
+        PointMass2<A, STRICT> m2;
+        float x1[2 * A], c1 = 0.0f;
+        f2 x2[NP][2 * A], c2[NP];
+        if constexpr (PACKED) {
+            m2.load(prob);
 #pragma unroll
-        for (int j = 0; j < SPT; ++j) {
-            c[j] = 0.0f;
+            for (int j = 0; j < NP; ++j) {
+                c2[j] = mk2(0.0f, 0.0f);
 #pragma unroll
-            for (int i = 0; i < 2 * A; ++i) x[j][i] = prob->x0[i];
+                for (int i = 0; i < 2 * A; ++i) x2[j][i] = mk2(prob->x0[i], prob->x0[i]);
+            }
+        } else {
+            m1.load(prob);
+#pragma unroll
+            for (int i = 0; i < 2 * A; ++i) x1[i] = prob->x0[i];
         }
         float *ep = eps + SPT * g;
 
         // one time step for all SPT samples given the eps vectors e[a][j]
         auto advance = [&](int t, const float (&e)[A][SPT]) {
-            float u[A], ui[A];
-            UStage<A>::fetch(smem_f, t, u, ui);
+            if constexpr (PACKED) {
+                f2 u[A], ui[A];
+                UStage2<A>::fetch(smem_f, t, u, ui);
 #pragma unroll
-            for (int j = 0; j < SPT; ++j) {
-                float ej[A];
+                for (int j = 0; j < NP; ++j) {
+                    f2 ej[A];
 #pragma unroll
-                for (int a = 0; a < A; ++a) ej[a] = e[a][j];
-                m.step(x[j], c[j], u, ui, ej);
+                    for (int a = 0; a < A; ++a) ej[a] = mk2(e[a][2 * j], e[a][(2 * j + 1) % SPT]);
+                    m2.step(x2[j], c2[j], u, ui, ej);
+                }
+            } else {
+                float u[A], ui[A], ej[A];
+                UStage<A>::fetch(smem_f, t, u, ui);
+#pragma unroll
+                for (int a = 0; a < A; ++a) ej[a] = e[a][0];
+                m1.step(x1, c1, u, ui, ej);
             }
         };
 
@@ -274,9 +409,18 @@ rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
         }
         // terminal cost on x[T] (charged on top of the last stage cost,
         // src/point_mass_gpu.cu:116)
+        float c[SPT];
+        if constexpr (PACKED) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                c2[j] = add2(c2[j], m2.state_cost(x2[j], mk2(0.0f, 0.0f)));
+                un2(c2[j], c[2 * j], c[(2 * j + 1) % SPT]);
+            }
+        } else {
+            c[0] = __fadd_rn(c1, m1.state_cost(x1, 0.0f));
+        }
 #pragma unroll
         for (int j = 0; j < SPT; ++j) {
-            c[j] = __fadd_rn(c[j], m.state_cost(x[j], 0.0f));
             S[SPT * g + j] = c[j];
             const long long k = (long long)(SPT * g) + j;
             if (k < k_local) {
@@ -949,7 +1093,8 @@ static cudaError_t launch_rollout_t(const LaunchCtx &c, float *eps, const float 
 {
     const size_t groups = (size_t)c.k_pad / SPT;
     const unsigned grid = (unsigned)((groups + 255) / 256);
-    const size_t smem = sizeof(float) * (size_t)c.horizon * UStage<A>::kStride;
+    const size_t smem = sizeof(float) * (size_t)c.horizon *
+                        (SPT >= 2 ? UStage2<A>::kStride : UStage<A>::kStride);
     rollout_kernel<A, STRICT, FUSED, SPT><<<grid, 256, smem, c.stream>>>(
         eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U, prob, S, ctl,
         (unsigned long long)c.k_offset, c.sampler);
@@ -1185,7 +1330,7 @@ cudaError_t configure_kernels(const LaunchCtx &c)
     }
     MPPI_DISPATCH_A(c.act_dim, e = configure_rollout_tma<kA>(c.horizon));
     if (e != cudaSuccess) return e;
-    const int ro = (int)(sizeof(float) * (size_t)c.horizon * 8);
+    const int ro = (int)(sizeof(float) * (size_t)c.horizon * 16);
     if (ro > 48 * 1024) {
         MPPI_DISPATCH_A(c.act_dim, e = configure_rollout<kA>(ro));
         if (e != cudaSuccess) return e;
