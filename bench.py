@@ -125,7 +125,7 @@ def cpu_reference_step(po, K, T, A, dt, goal, w, x0, U, eps, nthreads):
     ex = po.exp(S, 1.0, b)
     eta32, _ = po.eta(ex)
     wts = po.weights(S, 1.0, b, eta32)
-    un = po.update_act(U, wts, eps, K, T, A)
+    un = po.update_act(U, wts, eps, K, T, A, nthreads=nthreads)
     po.shift(un, T, A)
     return time.perf_counter() - t0
 
@@ -155,7 +155,8 @@ def run_reference(args, name, K, T, A, dt, goal, w):
     sample = (f"{Ks} of {K} samples per step (same T, A); rollout+cost = "
               + ("the reference's point_mass_gpu.cu+cost.cu compiled for the host (oracle/_ref), "
                  "OpenMP over samples" if kind == "reference" else "oracle port, OpenMP over samples")
-              + "; beta/exp/eta/weights/update_act_cpu/shift = oracle port, serial")
+              + "; beta/exp/eta/weights/shift = oracle port (serial), update_act_cpu = oracle port "
+                "split over column ranges (bit-identical to the serial loop)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,

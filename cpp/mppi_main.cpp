@@ -1,6 +1,6 @@
 // mppi_main.cpp -- the reference's driver loop (src/main.cu:220-399) on the B200 core.
 //
-//   mppi_main -c <config.yaml> [-t traj.csv] [--plant ideal|mjcf] [--steps N] [--samples K]
+//   mppi_main -c <config.yaml> [-t traj.csv] [-s step_prefix] [--plant ideal|mjcf] [--steps N] [--samples K]
 //             [--horizon T] [--honour-config] [--seed S] [--verify-config] [--quiet]
 //
 // Same sequence as the reference: parse config, build the plant and the controller, get_x,
@@ -49,9 +49,53 @@ static void to_csv_traj(const std::string &filename, const std::vector<std::vect
     std::cout << x.size() << " " << u.size() << std::endl;
 }
 
+// Per-step introspection dump, the reference's to_csv2 (src/main.cu:90-156) that its
+// scripts/plot_csv.py reads: one line per (sample, time) with state, noise, and -- on the
+// first sample's lines -- U after/before the update; cost and weight of sample n sit on
+// line n.  Column names are the reference's for the 2-D case (sample,x,y,x_dot,y_dot,e_x,e_y,
+// u[0],u[1],u_prev[0],u_prev[1],c,w) and are generalised with axis names otherwise.
+static void to_csv2(const std::string &filename, const float *x, const float *u, const float *u_prev,
+                    const float *e, const float *cost, const float *w, int sample, int size,
+                    int s_dim, int a_dim)
+{
+    static const char *axes[] = {"x", "y", "z", "w"};
+    std::cout << "Saving data to file...: " << std::flush;
+    std::ofstream out(filename);
+    out << "sample";
+    for (int i = 0; i < a_dim; ++i) out << "," << axes[i];
+    for (int i = 0; i < a_dim; ++i) out << "," << axes[i] << "_dot";
+    for (int i = 0; i < a_dim; ++i) out << ",e_" << axes[i];
+    for (int d = 0; d < a_dim; ++d) out << ",u[" << d << "]";
+    for (int d = 0; d < a_dim; ++d) out << ",u_prev[" << d << "]";
+    out << ",c,w" << std::endl;
+    for (int i = 0; i < sample; i++) {
+        for (int j = 0; j < size + 1; j++) {
+            out << i;
+            for (int d = 0; d < s_dim; ++d) out << "," << x[((size_t)i * (size + 1) + j) * s_dim + d];
+            for (int d = 0; d < a_dim; ++d) {
+                out << ",";
+                if (j < size) out << e[((size_t)i * size + j) * a_dim + d];
+                else out << " ";
+            }
+            for (int d = 0; d < a_dim; ++d) {
+                out << ",";
+                if (i < 1 && j < size) out << u[j * a_dim + d]; else out << " ";
+            }
+            for (int d = 0; d < a_dim; ++d) {
+                out << ",";
+                if (i < 1 && j < size) out << u_prev[j * a_dim + d]; else out << " ";
+            }
+            const long n = (long)i * (size + 1) + j;
+            if (n < sample) out << "," << cost[n] << "," << w[n];
+            out << std::endl;
+        }
+    }
+    std::cout << "Done" << std::endl;
+}
+
 int main(int argc, char **argv)
 {
-    std::string config_file = "config/point_mass2d.yaml", traj_file, plant_name = "ideal";
+    std::string config_file = "config/point_mass2d.yaml", traj_file, step_file, plant_name = "ideal";
     long max_steps = -1, samples_override = -1, horizon_override = -1;
     bool honour = false, verify = false, quiet = false;
     unsigned long long seed = 0;
@@ -63,6 +107,7 @@ int main(int argc, char **argv)
         };
         if (a == "-c" || a == "--config") config_file = next();
         else if (a == "-t" || a == "--traj-save") traj_file = next();
+        else if (a == "-s" || a == "--step-save") step_file = next();
         else if (a == "--plant") plant_name = next();
         else if (a == "--steps") max_steps = std::stol(next());
         else if (a == "--samples") samples_override = std::stol(next());
@@ -125,6 +170,14 @@ int main(int argc, char **argv)
         env.get_x(init_state.data());
         u.push_back(next_act);
         x.push_back(init_state);
+        if (!step_file.empty()) {        // save_step branch of the reference, src/main.cu:355-368
+            std::vector<float> h_x((size_t)n * (steps + 1) * state_dim), h_u((size_t)steps * act_dim),
+                h_e((size_t)n * steps * act_dim), cost(n), weight(n);
+            float beta = 0, nabla = 0;
+            model->get_inf(h_x.data(), h_u.data(), h_e.data(), cost.data(), &beta, &nabla, weight.data());
+            to_csv2(step_file + std::to_string(t), h_x.data(), h_u.data(), u_prev.data(), h_e.data(),
+                    cost.data(), weight.data(), n, steps, state_dim, act_dim);
+        }
         model->set_x(init_state.data());
         t += 1;
         if (max_steps > 0 && t >= max_steps) done = true;

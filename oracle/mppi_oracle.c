@@ -200,6 +200,31 @@ void oracle_update_act(float *u, const float *w, const float *e, int n, int t, i
                 u[j * a + i] += w[k] * e[(size_t)k * t * a + j * a + i];
 }
 
+/* update_act_cpu over disjoint column ranges in parallel: every u[j] still receives its K
+ * contributions in the order k = 0..n-1, so the result is bit-identical to the serial loop. */
+void oracle_update_act_mt(float *u, const float *w, const float *e, int n, int t, int a,
+                          int nthreads)
+{
+    const int ta = t * a;
+    (void)nthreads;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads > 1 ? nthreads : 1)
+#endif
+    {
+#ifdef _OPENMP
+        const int nt = omp_get_num_threads(), id = omp_get_thread_num();
+#else
+        const int nt = 1, id = 0;
+#endif
+        const int j0 = (int)((long long)ta * id / nt), j1 = (int)((long long)ta * (id + 1) / nt);
+        for (int k = 0; k < n; k++) {
+            const float wk = w[k];
+            const float *ek = e + (size_t)k * ta;
+            for (int j = j0; j < j1; j++) u[j] += wk * ek[j];
+        }
+    }
+}
+
 void oracle_update_act_f64(float *u, const float *w, const float *e, int n, int t, int a)
 {
     const int ta = t * a;

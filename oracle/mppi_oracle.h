@@ -75,6 +75,9 @@ void  oracle_weights(const float *S, int64_t K, float lambda, float beta, float 
 
 /* update_act_cpu, verbatim loop order k,t,a (src/test.cu:97-105) */
 void  oracle_update_act(float *u, const float *w, const float *e, int n, int t, int a);
+/* the same loop split over column ranges (bit-identical result, for the threaded baseline) */
+void  oracle_update_act_mt(float *u, const float *w, const float *e, int n, int t, int a,
+                           int nthreads);
 /* same sums accumulated in double then added to u (tolerance anchor) */
 void  oracle_update_act_f64(float *u, const float *w, const float *e, int n, int t, int a);
 

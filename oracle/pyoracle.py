@@ -71,6 +71,7 @@ def lib():
         L.oracle_weights.argtypes = [_f32p, C.c_int64, C.c_float, C.c_float, C.c_float, _f32p]
         L.oracle_update_act.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
         L.oracle_update_act_f64.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.oracle_update_act_mt.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle_shift.argtypes = [_f32p, C.c_int, C.c_int]
         L.oracle_step.argtypes = [PP, _f32p, _f32p, _f32p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -156,8 +157,11 @@ def weights(S, lam, b, e):
     return out
 
 
-def update_act(u, w, e, n, t, a, f64=False):
+def update_act(u, w, e, n, t, a, f64=False, nthreads=1):
     u = _f32(u).copy()
+    if nthreads > 1 and not f64:
+        lib().oracle_update_act_mt(u, _f32(w), _f32(e), int(n), int(t), int(a), int(nthreads))
+        return u
     fn = lib().oracle_update_act_f64 if f64 else lib().oracle_update_act
     fn(u, _f32(w), _f32(e), int(n), int(t), int(a))
     return u

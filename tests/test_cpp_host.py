@@ -74,3 +74,36 @@ def test_closed_loop_driver(tmp_path, cfg, plant):
         assert lines[0] == "x,y,vx,vy,ux,uy,size_x,size_u"       # src/main.cu:41-42
     assert lines[1].split(",")[-2:] == ["201", "200"]
     assert len(lines) == 1 + 200 + 1
+
+
+@pytest.mark.gpu
+def test_step_dump_matches_reference_csv_format_and_reproduces_the_update(tmp_path):
+    """-s: the reference's per-step dump (to_csv2, src/main.cu:90-156) that its
+    scripts/plot_csv.py consumes; the NumPy recomputation in that script
+    (scripts/plot_csv.py:77-108: cost, beta, exp, eta, weights) must reproduce the dumped
+    weights from the dumped costs."""
+    import csv
+
+    import numpy as np
+    _build()
+    prefix = tmp_path / "step"
+    r = subprocess.run([BIN, "-c", os.path.join(ROOT, "config", "point_mass2d.yaml"), "--samples", "300",
+                        "--horizon", "20", "--steps", "2", "--quiet", "-s", str(prefix)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rows = list(csv.DictReader(open(str(prefix) + "1")))
+    assert list(rows[0].keys()) == ["sample", "x", "y", "x_dot", "y_dot", "e_x", "e_y", "u[0]", "u[1]",
+                                    "u_prev[0]", "u_prev[1]", "c", "w"]
+    K, T = 300, 20
+    assert len(rows) == K * (T + 1)
+    c = np.array([float(rows[n]["c"]) for n in range(K)])
+    w = np.array([float(rows[n]["w"]) for n in range(K)])
+    ex = np.exp(-(c - c.min()))                       # lambda = 1, plot_csv.py:90-100
+    assert np.allclose(w, ex / ex.sum(), rtol=2e-5, atol=1e-9)
+    # U_next[t] = U_prev[t+1] + sum_k w_k e_k[t+1]   (update then shift)
+    e = np.array([[float(rows[k * (T + 1) + j]["e_x"]) for j in range(T)] for k in range(K)])
+    u_prev = np.array([float(rows[j]["u_prev[0]"]) for j in range(T)])
+    u_new = np.array([float(rows[j]["u[0]"]) for j in range(T)])
+    upd = u_prev + (w[:, None] * e).sum(0)
+    assert np.allclose(u_new[:-1], upd[1:], rtol=1e-4, atol=2e-6)
+    assert np.isclose(u_new[-1], upd[-1], rtol=1e-4, atol=2e-6)

@@ -108,6 +108,7 @@ def test_update_act_fixture_of_reference_test_cu(oracle, n):
         for k in range(n):
             want = (want + (w[k] * e2[k]).astype(np.float32)).astype(np.float32)
         assert np.array_equal(bits(got), bits(want))
+        assert np.array_equal(bits(oracle.update_act(u, w, e, n, t, a, nthreads=3)), bits(want))
         # and the double-accumulated anchor agrees to float rounding of the result
         d = oracle.update_act(u, w, e, n, t, a, f64=True)
         assert np.allclose(got, d, rtol=1e-5)
