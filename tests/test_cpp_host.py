@@ -99,11 +99,12 @@ def test_step_dump_matches_reference_csv_format_and_reproduces_the_update(tmp_pa
     c = np.array([float(rows[n]["c"]) for n in range(K)])
     w = np.array([float(rows[n]["w"]) for n in range(K)])
     ex = np.exp(-(c - c.min()))                       # lambda = 1, plot_csv.py:90-100
-    assert np.allclose(w, ex / ex.sum(), rtol=2e-5, atol=1e-9)
+    # the CSV carries 6 significant digits (default ostream precision, as the reference's)
+    assert np.allclose(w, ex / ex.sum(), rtol=5e-3, atol=1e-9)
     # U_next[t] = U_prev[t+1] + sum_k w_k e_k[t+1]   (update then shift)
     e = np.array([[float(rows[k * (T + 1) + j]["e_x"]) for j in range(T)] for k in range(K)])
     u_prev = np.array([float(rows[j]["u_prev[0]"]) for j in range(T)])
     u_new = np.array([float(rows[j]["u[0]"]) for j in range(T)])
     upd = u_prev + (w[:, None] * e).sum(0)
-    assert np.allclose(u_new[:-1], upd[1:], rtol=1e-4, atol=2e-6)
-    assert np.isclose(u_new[-1], upd[-1], rtol=1e-4, atol=2e-6)
+    assert np.allclose(u_new[:-1], upd[1:], rtol=1e-3, atol=1e-5)
+    assert np.isclose(u_new[-1], upd[-1], rtol=1e-3, atol=1e-5)

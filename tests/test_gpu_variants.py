@@ -1,0 +1,55 @@
+"""Every kernel variant that the size heuristics would otherwise only pick for some shapes,
+forced through environment overrides and checked against the oracle (compute-sanitizer is
+closed on this GPU pool, so out-of-bounds behaviour is probed with ragged shapes, every
+variant, and bit-exact comparisons instead)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import REF_CFG, bits, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [
+    ("ldg_spt1", {"MPPI_ROLLOUT_TMA": "0", "MPPI_ROLLOUT_SPT": "1"}, 0),
+    ("ldg_spt2_packed", {"MPPI_ROLLOUT_TMA": "0", "MPPI_ROLLOUT_SPT": "2"}, 0),
+    ("ldg_spt4_packed", {"MPPI_ROLLOUT_TMA": "0", "MPPI_ROLLOUT_SPT": "4"}, 0),
+    ("tma_w64", {"MPPI_ROLLOUT_TMA": "1", "MPPI_ROLLOUT_TMA_W": "64"}, 0),
+    ("tma_w128", {"MPPI_ROLLOUT_TMA": "1", "MPPI_ROLLOUT_TMA_W": "128"}, 0),
+    ("tma_w256", {"MPPI_ROLLOUT_TMA": "1", "MPPI_ROLLOUT_TMA_W": "256"}, 0),
+    ("split_kernels", {}, 64),
+    ("no_graph", {}, 16),
+]
+
+
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("name,env,flags", VARIANTS, ids=[v[0] for v in VARIANTS])
+@pytest.mark.parametrize("A,K,T", [(1, 1027, 37), (2, 2049, 23), (3, 3000, 50), (4, 777, 41), (3, 5, 3)])
+def test_variant_matches_oracle(oracle, name, env, flags, A, K, T, strict):
+    import mppi_gpu_b200 as m
+    cfg = REF_CFG[A]
+    x0, U, eps = make_inputs(K, T, A, seed=A * 1000 + K, sigma=0.2)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        ctl = m.PointMassModel(K, T, 0.1, 2 * A, A, flags=flags | (1 if strict else 0), lam=3.0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+    ctl.set_noise(eps)
+    na = ctl.get_act()
+    inf = ctl.get_inf(want_e=False)
+    info = ctl.step_info()
+    ctl.close()
+    p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], lam=3.0,
+                            arith=oracle.ARITH_STRICT if strict else oracle.ARITH_FMA)
+    ref = oracle.step(p, x0, U, eps)
+    assert np.array_equal(bits(inf["cost"]), bits(ref["S"])), np.abs(inf["cost"] - ref["S"]).max()
+    assert info["argmin"] == ref["argmin"] and bits(inf["beta"]) == bits(ref["beta"])
+    assert np.allclose(inf["u"].ravel(), ref["U"].ravel(), rtol=1e-5, atol=1e-6)
+    assert np.allclose(na, ref["next_act"], rtol=1e-5, atol=1e-6)
