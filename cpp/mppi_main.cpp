@@ -1,7 +1,7 @@
 // mppi_main.cpp -- the reference's driver loop (src/main.cu:220-399) on the B200 core.
 //
 //   mppi_main -c <config.yaml> [-t traj.csv] [-s step_prefix] [--plant ideal|mjcf] [--steps N] [--samples K]
-//             [--horizon T] [--honour-config] [--seed S] [--verify-config] [--quiet]
+//             [--horizon T] [--honour-config] [--seed S] [--devices 0,1,..] [--verify-config] [--quiet]
 //
 // Same sequence as the reference: parse config, build the plant and the controller, get_x,
 // zero action sequence, memcpy_set_data, then loop { get_u; time(get_act); simulate; get_x;
@@ -99,6 +99,7 @@ int main(int argc, char **argv)
     long max_steps = -1, samples_override = -1, horizon_override = -1;
     bool honour = false, verify = false, quiet = false;
     unsigned long long seed = 0;
+    std::vector<int> devices;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> std::string {
@@ -113,6 +114,16 @@ int main(int argc, char **argv)
         else if (a == "--samples") samples_override = std::stol(next());
         else if (a == "--horizon") horizon_override = std::stol(next());
         else if (a == "--seed") seed = std::stoull(next());
+        else if (a == "--devices") {           // e.g. --devices 0,1,2,3 : K sharded over GPUs
+            std::string list = next();
+            size_t pos = 0;
+            while (pos <= list.size()) {
+                size_t c = list.find(',', pos);
+                if (c == std::string::npos) c = list.size();
+                if (c > pos) devices.push_back(std::stoi(list.substr(pos, c - pos)));
+                pos = c + 1;
+            }
+        }
         else if (a == "--honour-config") honour = true;
         else if (a == "--verify-config") verify = true;
         else if (a == "--quiet") quiet = true;
@@ -140,6 +151,7 @@ int main(int argc, char **argv)
 
     PointMassModel::Options opt;
     opt.seed = seed;
+    if (!devices.empty()) { opt.devices = devices.data(); opt.num_devices = (int)devices.size(); }
     if (honour) {
         opt.lambda = cfg.lambda;
         opt.sigma = cfg.noise.data();

@@ -129,6 +129,14 @@ int mppi_params_default(mppi_params *p);
  * builds the CUDA graph of the control step. */
 int mppi_create(const mppi_params *params, mppi_handle **out);
 
+/* One controller over several GPUs of one process (the process model of a caller such as the
+ * reference's main.cu, which is a single process): K is sharded over devices[0..n-1], the
+ * shards exchange through peer memory (NVLink), every other call of this API works on the
+ * returned handle unchanged -- per-sample arrays of mppi_get_info / mppi_set_noise are the
+ * full [K] arrays.  params->device/rank/world_size/comm are ignored. */
+int mppi_create_multi(const mppi_params *params, const int *devices, int num_devices,
+                      mppi_handle **out);
+
 /* == delete model (src/point_mass.cu:108-127) */
 int mppi_destroy(mppi_handle *h);
 

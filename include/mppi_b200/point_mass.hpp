@@ -41,6 +41,8 @@ public:
         unsigned long long seed = 0;
         unsigned flags = 0;                // extra MPPI_FLAG_* bits
         int device = 0;
+        const int *devices = nullptr;      // non-null: shard K over these GPUs (one process)
+        int num_devices = 0;
     };
 
     PointMassModel(int nb_sim, int steps, float dt, int state_dim, int act_dim,
@@ -71,7 +73,10 @@ public:
         if (o.init_act) p.flags |= MPPI_FLAG_REINIT_INIT_ACT;
         if (o.max_act) p.flags |= MPPI_FLAG_CLAMP_ACTIONS;
         _n_sim = nb_sim; _steps = steps; _state_dim = state_dim; _act_dim = act_dim;
-        check(mppi_create(&p, &_h), __LINE__);
+        if (o.devices && o.num_devices > 0)
+            check(mppi_create_multi(&p, o.devices, o.num_devices, &_h), __LINE__);
+        else
+            check(mppi_create(&p, &_h), __LINE__);
     }
 
     ~PointMassModel() { if (_h) mppi_destroy(_h); }

@@ -35,7 +35,7 @@ K_SAMPLE, K_ROLLOUT, K_COMM_MIN, K_WEIGHTS, K_AVERAGE, K_COMM_SUM, K_FINALIZE, K
 
 # every symbol include/mppi_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "mppi_params_default", "mppi_create", "mppi_destroy", "mppi_set_problem", "mppi_set_state",
+    "mppi_params_default", "mppi_create", "mppi_create_multi", "mppi_destroy", "mppi_set_problem", "mppi_set_state",
     "mppi_step", "mppi_step_enqueue", "mppi_step_wait", "mppi_get_u", "mppi_set_u",
     "mppi_get_info", "mppi_get_step_info", "mppi_set_noise", "mppi_set_noise_mode",
     "mppi_sample_only", "mppi_shard_range", "mppi_local_samples", "mppi_timer_start", "mppi_timer_stop",
@@ -101,6 +101,7 @@ def load():
     L.mppi_kernel_name.argtypes = [C.c_int]
     L.mppi_params_default.argtypes = [C.POINTER(MppiParams)]
     L.mppi_create.argtypes = [C.POINTER(MppiParams), C.POINTER(H)]
+    L.mppi_create_multi.argtypes = [C.POINTER(MppiParams), C.POINTER(C.c_int), C.c_int, C.POINTER(H)]
     L.mppi_destroy.argtypes = [H]
     L.mppi_set_problem.argtypes = [H, fp, fp, fp, fp]
     L.mppi_set_state.argtypes = [H, fp]

@@ -20,7 +20,7 @@ class PointMassModel:
 
     def __init__(self, nb_sim, steps, dt, state_dim, act_dim, verbose=False, *, lam=1.0,
                  sigma=0.025, inv_sigma=1.0, init_act=0.0, max_act=1.0, seed=0, flags=0,
-                 device=0, rank=0, world_size=1, comm_id=None, comm=None):
+                 device=0, rank=0, world_size=1, comm_id=None, comm=None, devices=None):
         self._lib = capi.load()
         p = capi.MppiParams()
         capi.check(self._lib.mppi_params_default(C.byref(p)))
@@ -43,7 +43,12 @@ class PointMassModel:
                     p.comm_id[i] = b
         self.params = p
         self._h = C.c_void_p()
-        capi.check(self._lib.mppi_create(C.byref(p), C.byref(self._h)))
+        if devices is not None:
+            # one process driving several GPUs: K sharded over `devices`, peer-memory exchange
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            capi.check(self._lib.mppi_create_multi(C.byref(p), devs, len(devices), C.byref(self._h)))
+        else:
+            capi.check(self._lib.mppi_create(C.byref(p), C.byref(self._h)))
         self.K, self.T, self.S, self.A = int(nb_sim), int(steps), int(state_dim), int(act_dim)
         kl, ko = C.c_int64(), C.c_int64()
         capi.check(self._lib.mppi_local_samples(self._h, C.byref(kl), C.byref(ko)))

@@ -73,11 +73,14 @@ struct mppi_handle {
     unsigned long long *d_mailbox = nullptr;              // MPPI_COMM_P2P: this rank's mailbox
     unsigned long long *peer_mb[kMaxWorld] = {};          // every rank's mailbox mapped here
     bool p2p_connected = false;
+    bool peers_are_ipc = false;                           // peer_mb[] came from cudaIpcOpenMemHandle
+    std::vector<mppi_handle *> children;                  // single-process multi-device group
 
     bool problem_set = false;
     bool injected = false;
     bool profiling = false;
     bool pending = false;
+    bool prof_pending = false, prof_sampled = false;      // profiling times to collect at wait
 
     cudaEvent_t ev[MPPI_K_COUNT + 1] = {};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -248,6 +251,8 @@ int mppi_comm_unique_id(uint8_t id[MPPI_COMM_ID_BYTES])
 
 int mppi_comm_p2p_handle(mppi_handle *h, uint8_t out[MPPI_P2P_HANDLE_BYTES])
 {
+    if (h && !h->children.empty())
+        return fail(MPPI_ERR_INVALID, "a single-process device group connects its shards itself");
     int rc = check_handle(h);
     if (rc) return rc;
     if (!p2p(h) || !out) return fail(MPPI_ERR_INVALID, "handle was not created with MPPI_COMM_P2P");
@@ -261,6 +266,8 @@ int mppi_comm_p2p_handle(mppi_handle *h, uint8_t out[MPPI_P2P_HANDLE_BYTES])
 
 int mppi_comm_p2p_connect(mppi_handle *h, const uint8_t *handles)
 {
+    if (h && !h->children.empty())
+        return fail(MPPI_ERR_INVALID, "a single-process device group connects its shards itself");
     int rc = check_handle(h);
     if (rc) return rc;
     if (!p2p(h) || !handles) return fail(MPPI_ERR_INVALID, "handle was not created with MPPI_COMM_P2P");
@@ -274,6 +281,7 @@ int mppi_comm_p2p_connect(mppi_handle *h, const uint8_t *handles)
             return fail(MPPI_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
         h->peer_mb[r] = static_cast<unsigned long long *>(ptr);
     }
+    h->peers_are_ipc = true;
     h->p2p_connected = true;
     return MPPI_OK;
 }
@@ -281,10 +289,18 @@ int mppi_comm_p2p_connect(mppi_handle *h, const uint8_t *handles)
 int mppi_destroy(mppi_handle *h)
 {
     if (!h) return MPPI_OK;
+    if (!h->children.empty()) {
+        for (mppi_handle *c : h->children)            // all shards idle before any memory goes
+            if (c && c->stream) { cudaSetDevice(c->p.device); cudaStreamSynchronize(c->stream); }
+        for (mppi_handle *c : h->children) mppi_destroy(c);
+        delete h;
+        return MPPI_OK;
+    }
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int r = 0; r < kMaxWorld; ++r)
-        if (h->peer_mb[r] && h->peer_mb[r] != h->d_mailbox) cudaIpcCloseMemHandle(h->peer_mb[r]);
+        if (h->peers_are_ipc && h->peer_mb[r] && h->peer_mb[r] != h->d_mailbox)
+            cudaIpcCloseMemHandle(h->peer_mb[r]);
     cudaFree(h->d_mailbox);
     for (auto &g : h->graph_exec) if (g) cudaGraphExecDestroy(g);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -473,6 +489,62 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     return MPPI_OK;
 }
 
+int mppi_create_multi(const mppi_params *params, const int *devices, int num_devices,
+                      mppi_handle **out)
+{
+    if (!params || !devices || !out) return fail(MPPI_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (num_devices < 1 || num_devices > kMaxWorld)
+        return fail(MPPI_ERR_INVALID, "num_devices %d not in [1,%d]", num_devices, kMaxWorld);
+    if (params->struct_size != sizeof(mppi_params))
+        return fail(MPPI_ERR_INVALID, "mppi_params.struct_size mismatch (ABI)");
+    if (num_devices == 1) {
+        mppi_params p1 = *params;
+        p1.device = devices[0]; p1.rank = 0; p1.world_size = 1; p1.comm = MPPI_COMM_NONE;
+        return mppi_create(&p1, out);
+    }
+    for (int i = 0; i < num_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j])
+                return fail(MPPI_ERR_INVALID, "device %d listed twice", devices[i]);
+    mppi_handle *g = new mppi_handle();
+    g->p = *params;
+    g->p.world_size = num_devices;
+    g->p.comm = MPPI_COMM_P2P;
+    g->R = params->horizon * params->act_dim;
+    g->S = params->state_dim;
+    int rc = MPPI_OK;
+    for (int i = 0; i < num_devices && rc == MPPI_OK; ++i) {
+        mppi_params pc = *params;
+        pc.device = devices[i]; pc.rank = i; pc.world_size = num_devices; pc.comm = MPPI_COMM_P2P;
+        mppi_handle *c = nullptr;
+        rc = mppi_create(&pc, &c);
+        if (rc == MPPI_OK) g->children.push_back(c);
+    }
+    // direct peer mappings between all pairs (same process: no IPC needed)
+    for (int i = 0; i < num_devices && rc == MPPI_OK; ++i) {
+        cudaSetDevice(devices[i]);
+        for (int j = 0; j < num_devices && rc == MPPI_OK; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+            if (!can) { rc = fail(MPPI_ERR_COMM, "device %d cannot access device %d", devices[i], devices[j]); break; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess)
+                rc = fail(MPPI_ERR_COMM, "cudaDeviceEnablePeerAccess(%d->%d) -> %s", devices[i],
+                          devices[j], cudaGetErrorString(e));
+        }
+    }
+    if (rc != MPPI_OK) { mppi_destroy(g); return rc; }
+    for (int i = 0; i < num_devices; ++i) {
+        for (int j = 0; j < num_devices; ++j) g->children[i]->peer_mb[j] = g->children[j]->d_mailbox;
+        g->children[i]->p2p_connected = true;
+    }
+    *out = g;
+    return MPPI_OK;
+}
+
 int mppi_shard_range(int64_t samples, int rank, int world_size, int64_t *k_begin, int64_t *k_end)
 {
     if (samples < 1 || world_size < 1 || rank < 0 || rank >= world_size || !k_begin || !k_end)
@@ -487,6 +559,11 @@ int mppi_shard_range(int64_t samples, int rank, int world_size, int64_t *k_begin
 
 int mppi_local_samples(mppi_handle *h, int64_t *k_local, int64_t *k_offset)
 {
+    if (h && !h->children.empty()) {
+        if (k_local) *k_local = h->p.samples;
+        if (k_offset) *k_offset = 0;
+        return MPPI_OK;
+    }
     if (!h) return fail(MPPI_ERR_INVALID, "null handle");
     if (k_local) *k_local = h->ctx.k_local;
     if (k_offset) *k_offset = h->ctx.k_offset;
@@ -496,6 +573,13 @@ int mppi_local_samples(mppi_handle *h, int64_t *k_local, int64_t *k_offset)
 int mppi_set_problem(mppi_handle *h, const float *x0, const float *u, const float *goal,
                      const float *w)
 {
+    if (h && !h->children.empty()) {
+        for (mppi_handle *c : h->children) {
+            int rcc = mppi_set_problem(c, x0, u, goal, w);
+            if (rcc) return rcc;
+        }
+        return MPPI_OK;
+    }
     int rc = check_handle(h);
     if (rc) return rc;
     if (!x0 || !u || !goal || !w) return fail(MPPI_ERR_INVALID, "null argument");
@@ -515,6 +599,10 @@ int mppi_set_problem(mppi_handle *h, const float *x0, const float *u, const floa
 
 int mppi_set_u(mppi_handle *h, const float *u)
 {
+    if (h && !h->children.empty()) {
+        for (mppi_handle *c : h->children) { int rcc = mppi_set_u(c, u); if (rcc) return rcc; }
+        return MPPI_OK;
+    }
     int rc = check_handle(h);
     if (rc) return rc;
     if (!u) return fail(MPPI_ERR_INVALID, "null argument");
@@ -525,6 +613,10 @@ int mppi_set_u(mppi_handle *h, const float *u)
 
 int mppi_set_state(mppi_handle *h, const float *x)
 {
+    if (h && !h->children.empty()) {
+        for (mppi_handle *c : h->children) { int rcc = mppi_set_state(c, x); if (rcc) return rcc; }
+        return MPPI_OK;
+    }
     int rc = check_handle(h);
     if (rc) return rc;
     if (!x) return fail(MPPI_ERR_INVALID, "null argument");
@@ -538,6 +630,12 @@ int mppi_set_state(mppi_handle *h, const float *x)
 
 int mppi_step_enqueue(mppi_handle *h)
 {
+    if (h && !h->children.empty()) {
+        // every shard's graph is enqueued before anything waits: the shards meet in the
+        // peer-mailbox exchanges on the devices
+        for (mppi_handle *c : h->children) { int rcc = mppi_step_enqueue(c); if (rcc) return rcc; }
+        return MPPI_OK;
+    }
     int rc = check_handle(h);
     if (rc) return rc;
     if (!h->problem_set) return fail(MPPI_ERR_STATE, "mppi_step before mppi_set_problem");
@@ -548,21 +646,7 @@ int mppi_step_enqueue(mppi_handle *h)
     if (h->profiling || (h->p.flags & MPPI_FLAG_NO_GRAPH)) {
         rc = enqueue_chain(h, sample, h->profiling ? h->ev : nullptr);
         if (rc) return rc;
-        if (h->profiling) {
-            CK(cudaStreamSynchronize(h->stream));
-            // event i+1 closes stage i of {sample, rollout, comm_min, weights, average,
-            // comm_sum, finalize(+D2H)}
-            for (int i = 0; i < MPPI_K_COUNT; ++i) {
-                float ms = 0.f;
-                CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
-                const bool split = (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) != 0;
-                const bool ran = (i == MPPI_K_SAMPLE) ? (sample && !fused(h))
-                               : (i == MPPI_K_COMM_MIN || i == MPPI_K_COMM_SUM) ? multi(h)
-                               : (i == MPPI_K_WEIGHTS) ? split
-                               : (i == MPPI_K_FINALIZE) ? ((split || multi(h)) && !p2p(h)) : true;
-                if (ran) { h->ms_sum[i] += ms; h->launches[i] += 1; }
-            }
-        }
+        if (h->profiling) { h->prof_pending = true; h->prof_sampled = sample; }
     } else {
         if (!h->graph_exec[which] && (rc = build_graph(h, which)) != MPPI_OK) return rc;
         CK(cudaGraphLaunch(h->graph_exec[which], h->stream));
@@ -574,10 +658,34 @@ int mppi_step_enqueue(mppi_handle *h)
 
 int mppi_step_wait(mppi_handle *h, float *next_act)
 {
+    if (h && !h->children.empty()) {
+        int first_err = MPPI_OK;
+        for (size_t i = 0; i < h->children.size(); ++i) {
+            int rcc = mppi_step_wait(h->children[i], i == 0 ? next_act : nullptr);
+            if (rcc && !first_err) first_err = rcc;
+        }
+        return first_err;
+    }
     int rc = check_handle(h);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
     h->pending = false;
+    if (h->prof_pending) {
+        // event i+1 closes stage i of {sample, rollout, comm_min, weights, average,
+        // comm_sum, finalize(+D2H)}
+        h->prof_pending = false;
+        const bool sample = h->prof_sampled;
+        for (int i = 0; i < MPPI_K_COUNT; ++i) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+            const bool split = (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) != 0;
+            const bool ran = (i == MPPI_K_SAMPLE) ? (sample && !fused(h))
+                           : (i == MPPI_K_COMM_MIN || i == MPPI_K_COMM_SUM) ? multi(h)
+                           : (i == MPPI_K_WEIGHTS) ? split
+                           : (i == MPPI_K_FINALIZE) ? ((split || multi(h)) && !p2p(h)) : true;
+            if (ran) { h->ms_sum[i] += ms; h->launches[i] += 1; }
+        }
+    }
     if (next_act)
         for (int a = 0; a < h->p.act_dim; ++a) next_act[a] = h->h_next[a];
     if (h->h_next[kMaxAct] != 0.0f)
@@ -594,6 +702,7 @@ int mppi_step(mppi_handle *h, float *next_act)
 
 int mppi_get_u(mppi_handle *h, float *u)
 {
+    if (h && !h->children.empty()) return mppi_get_u(h->children[0], u);
     int rc = check_handle(h);
     if (rc) return rc;
     if (!u) return fail(MPPI_ERR_INVALID, "null argument");
@@ -604,6 +713,7 @@ int mppi_get_u(mppi_handle *h, float *u)
 
 int mppi_get_step_info(mppi_handle *h, mppi_step_info *info)
 {
+    if (h && !h->children.empty()) return mppi_get_step_info(h->children[0], info);
     int rc = check_handle(h);
     if (rc) return rc;
     if (!info) return fail(MPPI_ERR_INVALID, "null argument");
@@ -621,6 +731,20 @@ int mppi_get_step_info(mppi_handle *h, mppi_step_info *info)
 int mppi_get_info(mppi_handle *h, float *x, float *u, float *e, float *cost, float *beta,
                   float *nabla, float *weight)
 {
+    if (h && !h->children.empty()) {
+        // shards are contiguous in k: every per-sample array is filled shard by shard
+        for (size_t i = 0; i < h->children.size(); ++i) {
+            mppi_handle *c = h->children[i];
+            const size_t k0 = (size_t)c->ctx.k_offset, R = (size_t)c->R, S = (size_t)c->S;
+            const size_t T1 = (size_t)c->p.horizon + 1;
+            int rcc = mppi_get_info(c, x ? x + k0 * T1 * S : nullptr, i == 0 ? u : nullptr,
+                                    e ? e + k0 * R : nullptr, cost ? cost + k0 : nullptr,
+                                    i == 0 ? beta : nullptr, i == 0 ? nabla : nullptr,
+                                    weight ? weight + k0 : nullptr);
+            if (rcc) return rcc;
+        }
+        return MPPI_OK;
+    }
     int rc = check_handle(h);
     if (rc) return rc;
     const LaunchCtx &c = h->ctx;
@@ -676,6 +800,10 @@ int mppi_get_info(mppi_handle *h, float *x, float *u, float *e, float *cost, flo
 
 int mppi_set_noise_mode(mppi_handle *h, int injected)
 {
+    if (h && !h->children.empty()) {
+        for (mppi_handle *c : h->children) mppi_set_noise_mode(c, injected);
+        return MPPI_OK;
+    }
     if (!h) return fail(MPPI_ERR_INVALID, "null handle");
     h->injected = injected != 0;
     return MPPI_OK;
@@ -683,6 +811,14 @@ int mppi_set_noise_mode(mppi_handle *h, int injected)
 
 int mppi_set_noise(mppi_handle *h, const float *e)
 {
+    if (h && !h->children.empty()) {
+        if (!e) return fail(MPPI_ERR_INVALID, "null argument");
+        for (mppi_handle *c : h->children) {
+            int rcc = mppi_set_noise(c, e + (size_t)c->ctx.k_offset * c->R);
+            if (rcc) return rcc;
+        }
+        return MPPI_OK;
+    }
     int rc = check_handle(h);
     if (rc) return rc;
     if (!e) return fail(MPPI_ERR_INVALID, "null argument");
@@ -702,6 +838,10 @@ int mppi_set_noise(mppi_handle *h, const float *e)
 
 int mppi_sample_only(mppi_handle *h, uint64_t step)
 {
+    if (h && !h->children.empty()) {
+        for (mppi_handle *c : h->children) { int rcc = mppi_sample_only(c, step); if (rcc) return rcc; }
+        return MPPI_OK;
+    }
     int rc = check_handle(h);
     if (rc) return rc;
     CK(launch_sample(h->ctx, h->d_eps, h->d_ctl, true, step));
@@ -712,6 +852,7 @@ int mppi_sample_only(mppi_handle *h, uint64_t step)
 
 int mppi_timer_start(mppi_handle *h)
 {
+    if (h && !h->children.empty()) return mppi_timer_start(h->children[0]);
     int rc = check_handle(h);
     if (rc) return rc;
     CK(cudaEventRecord(h->t0, h->stream));
@@ -720,6 +861,7 @@ int mppi_timer_start(mppi_handle *h)
 
 int mppi_timer_stop(mppi_handle *h, float *elapsed_ms)
 {
+    if (h && !h->children.empty()) return mppi_timer_stop(h->children[0], elapsed_ms);
     int rc = check_handle(h);
     if (rc) return rc;
     CK(cudaEventRecord(h->t1, h->stream));
@@ -732,6 +874,10 @@ int mppi_timer_stop(mppi_handle *h, float *elapsed_ms)
 
 int mppi_set_profiling(mppi_handle *h, int enabled)
 {
+    if (h && !h->children.empty()) {
+        for (mppi_handle *c : h->children) mppi_set_profiling(c, enabled);
+        return MPPI_OK;
+    }
     if (!h) return fail(MPPI_ERR_INVALID, "null handle");
     h->profiling = enabled != 0;
     return MPPI_OK;
@@ -739,6 +885,10 @@ int mppi_set_profiling(mppi_handle *h, int enabled)
 
 int mppi_get_kernel_times(mppi_handle *h, double *ms_sum, int64_t *launches)
 {
+    if (h && !h->children.empty()) {
+        for (size_t i = 1; i < h->children.size(); ++i) mppi_get_kernel_times(h->children[i], nullptr, nullptr);
+        return mppi_get_kernel_times(h->children[0], ms_sum, launches);
+    }
     if (!h) return fail(MPPI_ERR_INVALID, "null handle");
     for (int i = 0; i < MPPI_K_COUNT; ++i) {
         if (ms_sum) ms_sum[i] = h->ms_sum[i];
@@ -751,6 +901,11 @@ int mppi_get_kernel_times(mppi_handle *h, double *ms_sum, int64_t *launches)
 
 int mppi_get_launch_count(mppi_handle *h, int64_t *launches)
 {
+    if (h && launches && !h->children.empty()) {
+        *launches = 0;
+        for (mppi_handle *c : h->children) *launches += c->total_launches;
+        return MPPI_OK;
+    }
     if (!h || !launches) return fail(MPPI_ERR_INVALID, "null argument");
     *launches = h->total_launches;
     return MPPI_OK;
