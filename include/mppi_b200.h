@@ -63,6 +63,14 @@ extern "C" {
                                                their own instead of inside the averaging
                                                kernel (4): per-part profiling                */
 
+#define MPPI_FLAG_STEP_KERNEL     (1u << 7)  /* the whole control step as ONE persistent kernel:
+                                               sampling + rollout warps and the TMA-fed
+                                               weighted-average warps share every SM, so the
+                                               issue-bound and the HBM-bound halves overlap.
+                                               Sampled noise, single shard, T*A small enough for
+                                               the shared-memory row sums; otherwise the step
+                                               silently uses the kernel chain                */
+
 /* mppi_params.comm */
 #define MPPI_COMM_NONE  0   /* single shard                                          */
 #define MPPI_COMM_NCCL  1   /* ncclAllReduce(min) for beta, ncclAllReduce(sum) for the

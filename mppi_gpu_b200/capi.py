@@ -27,6 +27,7 @@ FLAG_REINIT_INIT_ACT = 1 << 3
 FLAG_NO_GRAPH = 1 << 4
 FLAG_FUSED_SAMPLING = 1 << 5
 FLAG_SPLIT_KERNELS = 1 << 6
+FLAG_STEP_KERNEL = 1 << 7
 
 COMM_NONE, COMM_NCCL, COMM_P2P = 0, 1, 2
 P2P_HANDLE_BYTES = 64

@@ -185,6 +185,32 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap)
 }
 
 // ---------------------------------------------------------------------------------
+// intra-CTA signalling through shared memory (step kernel: rollout warp -> producer warp)
+// and the generic -> async proxy fence a TMA load needs to see global data written by
+// ordinary stores of the same kernel
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_cta_shared_u32(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" :: "r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_cta_shared_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all()
+{
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ float warp_min_f(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------
 // system-scope accesses for the peer-mailbox exchange over NVLink (multi-GPU)
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)

@@ -68,6 +68,8 @@ struct mppi_handle {
 
     CUtensorMap tmap{};        // average kernel: box {256, kAvgTileR}
     CUtensorMap tmap_ro{};     // TMA rollout: box {256, TT*A}
+    CUtensorMap tmap_st{};     // step kernel: box {128, 40}
+    float *d_part = nullptr;   // step kernel: one {ref, eta, row sums} record per CTA
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // [0] sampling, [1] injected noise
     NcclComm comm;
     unsigned long long *d_mailbox = nullptr;              // MPPI_COMM_P2P: this rank's mailbox
@@ -94,6 +96,12 @@ namespace {
 bool multi(const mppi_handle *h) { return h->p.world_size > 1; }
 bool p2p(const mppi_handle *h) { return multi(h) && h->p.comm == MPPI_COMM_P2P; }
 bool fused(const mppi_handle *h) { return (h->p.flags & MPPI_FLAG_FUSED_SAMPLING) != 0; }
+// the one-kernel step: sampled noise, single shard, row sums fit in shared memory
+bool one_kernel(const mppi_handle *h, bool sample)
+{
+    return sample && (h->p.flags & MPPI_FLAG_STEP_KERNEL) && !multi(h) &&
+           !(h->p.flags & MPPI_FLAG_SPLIT_KERNELS) && h->d_part != nullptr;
+}
 
 int encode_tmap(mppi_handle *h, CUtensorMap *out, int box_cols, int box_rows)
 {
@@ -129,6 +137,17 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
         return evs ? cudaEventRecord(evs[ei++], c.stream) : cudaSuccess;
     };
     CK(mark());
+    if (one_kernel(h, sample)) {
+        for (int i = 0; i < MPPI_K_AVERAGE; ++i) CK(mark());     // the time is booked on "average"
+        CK(launch_step(c, h->tmap_st, h->d_eps, h->d_U, h->d_prob, h->d_S, h->d_ctl, h->d_part,
+                       h->d_acc, h->d_Uprev, h->d_next, h->p.flags));
+        CK(mark());
+        CK(mark());
+        CK(cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * (kMaxAct + 1), cudaMemcpyDeviceToHost,
+                           c.stream));
+        CK(mark());
+        return MPPI_OK;
+    }
     if (sample && !fused(h)) CK(launch_sample(c, h->d_eps, h->d_ctl, false, 0));
     CK(mark());
     if (c.rollout_tma && !(sample && fused(h)))
@@ -171,6 +190,7 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
 
 int kernels_per_step(const mppi_handle *h, bool sample)
 {
+    if (one_kernel(h, sample)) return 1;
     int n = 2;                                  // rollout, average(+weights,+finalize)
     if (sample && !fused(h)) n += 1;            // sampling
     if (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) n += 1;      // separate weights kernel
@@ -307,7 +327,7 @@ int mppi_destroy(mppi_handle *h)
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     cudaFree(h->d_eps); cudaFree(h->d_S); cudaFree(h->d_wt); cudaFree(h->d_acc);
-    cudaFree(h->d_U); cudaFree(h->d_Uprev);
+    cudaFree(h->d_U); cudaFree(h->d_Uprev); cudaFree(h->d_part);
     cudaFree(h->d_next); cudaFree(h->d_prob); cudaFree(h->d_ctl);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_next) cudaFreeHost(h->h_next);
@@ -449,6 +469,11 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     CKH(cudaEventCreate(&h->t0));
     CKH(cudaEventCreate(&h->t1));
     CKH(configure_kernels(c));
+    if ((p.flags & MPPI_FLAG_STEP_KERNEL) && step_kernel_supported(p.horizon, p.act_dim)) {
+        CKH(configure_step(c));
+        CKH(cudaMalloc(&h->d_part, sizeof(float) * step_part_floats(c)));
+        CKH(cudaMemsetAsync(h->d_part, 0, sizeof(float) * step_part_floats(c), h->stream));
+    }
 #undef CKH
 
     // problem constants: gains as the reference forms them (src/point_mass.cu:46-51)
@@ -469,6 +494,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     }
     if ((rc = upload_problem(h)) != MPPI_OK) { mppi_destroy(h); return rc; }
     if ((rc = encode_tmap(h, &h->tmap, kAvgTileK, kAvgTileR)) != MPPI_OK) { mppi_destroy(h); return rc; }
+    if ((rc = encode_tmap(h, &h->tmap_st, kStepTileK, kStepTileR)) != MPPI_OK) { mppi_destroy(h); return rc; }
     if ((rc = encode_tmap(h, &h->tmap_ro, c.rollout_tma_width, rollout_tma_rows(p.act_dim))) != MPPI_OK) { mppi_destroy(h); return rc; }
 
     if (multi(h) && p.comm == MPPI_COMM_NCCL) {

@@ -87,6 +87,18 @@ cudaError_t launch_norm_weights(const LaunchCtx &c, const float *S, float lambda
 cudaError_t launch_trajectories(const LaunchCtx &c, const float *eps, const float *U_prev,
                                 const ProblemDev *prob, float *x_out);
 
+// (1-5) the whole control step in one persistent warp-specialised kernel (step.cu): fused
+//       sampling + rollout warps, TMA producer and consumer warps of the weighted average on
+//       every SM at once, last CTA merges and applies the U update.  tmap: box {128, 40}.
+//       part: step_part_floats() floats of scratch (one record per CTA).
+bool step_kernel_supported(int T, int A);
+size_t step_part_floats(const LaunchCtx &c);
+cudaError_t configure_step(const LaunchCtx &c);
+cudaError_t launch_step(const LaunchCtx &c, const CUtensorMap &tmap, float *eps, float *U,
+                        const ProblemDev *prob, float *S, CtlDev *ctl, float *part, long long *acc,
+                        float *U_prev, float *next_act, unsigned flags);
+constexpr int kStepTileK = 128, kStepTileR = 40;   // its TMA box
+
 // reset the control block (min key armed, step 0)
 cudaError_t launch_clear_ctl(const LaunchCtx &c, CtlDev *ctl);
 

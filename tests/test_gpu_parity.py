@@ -33,7 +33,8 @@ def _close(a, b, tol=RTOL_U):
 def _assert_noise_close(e, want, sigma):
     d = np.abs(e - want) / sigma
     assert d.max() < 1e-3, d.max()
-    assert np.mean(d > 2e-5) <= 1e-5, np.mean(d > 2e-5)
+    # (at most 2 draws for small arrays, where one draw already exceeds 1e-5 of them)
+    assert np.mean(d > 2e-5) <= max(1e-5, 2.0 / d.size), np.mean(d > 2e-5)
 
 
 @pytest.fixture(scope="module")
