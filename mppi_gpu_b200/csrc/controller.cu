@@ -469,7 +469,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     CKH(cudaEventCreate(&h->t0));
     CKH(cudaEventCreate(&h->t1));
     CKH(configure_kernels(c));
-    if ((p.flags & MPPI_FLAG_STEP_KERNEL) && step_kernel_supported(p.horizon, p.act_dim)) {
+    if ((p.flags & MPPI_FLAG_STEP_KERNEL) && step_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms)) {
         CKH(configure_step(c));
         CKH(cudaMalloc(&h->d_part, sizeof(float) * step_part_floats(c)));
         CKH(cudaMemsetAsync(h->d_part, 0, sizeof(float) * step_part_floats(c), h->stream));

@@ -91,7 +91,7 @@ cudaError_t launch_trajectories(const LaunchCtx &c, const float *eps, const floa
 //       sampling + rollout warps, TMA producer and consumer warps of the weighted average on
 //       every SM at once, last CTA merges and applies the U update.  tmap: box {128, 40}.
 //       part: step_part_floats() floats of scratch (one record per CTA).
-bool step_kernel_supported(int T, int A);
+bool step_kernel_supported(int T, int A, long long k_pad, int num_sms);
 size_t step_part_floats(const LaunchCtx &c);
 cudaError_t configure_step(const LaunchCtx &c);
 cudaError_t launch_step(const LaunchCtx &c, const CUtensorMap &tmap, float *eps, float *U,

@@ -10,23 +10,32 @@
 // consumer warps fold them into the weighted sums.  The reference needs ~3T+8 launches for
 // the same work (PointMassModel::get_act, src/point_mass.cu:129-203).
 //
-// Roles inside a CTA (one CTA per SM):
+// Roles inside a CTA (one CTA per SM, 20 warps):
 //   warps [0, NR)        rollout: per tile of 128 samples (one Philox quad per lane) sample
 //                        eps, store it, integrate, store S, atomicMin the packed (S, k) key,
-//                        then publish "my round n is complete" in shared memory.
-//   warp  NR             producer: waits, in a FIXED order, for the tiles of its own CTA,
-//                        turns the tile's costs into weights relative to the CTA's running
-//                        minimum `ref` (online softmax: when a tile lowers ref, the weighted
-//                        sums gathered so far are rescaled by exp(-(ref_old-ref_new)/lambda)),
-//                        and issues one cp.async.bulk.tensor.2d per [40 rows x 128 samples] box.
-//   warps [NR+1, NR+5)   consumers: warp c owns rows {c, c+4, ...} of every box; each lane
-//                        keeps its own partial of every row it owns in shared memory
-//                        (s_part[row][lane]) -- no shuffles in the steady state.
-// Tile -> (CTA, warp, round) is a static function of the tile index and the consumption order
-// is fixed, so every CTA's sums are formed in the same order on every run: results are
-// bitwise reproducible.  At the end each CTA writes {ref, eta, row sums} to a record; the
-// last CTA (ticket) merges the records in CTA order, rescaling each by exp(-(ref_c-beta)/lambda),
-// converts to the fixed-point accumulators and applies the U update (part 5).
+//                        then flag the tile as complete in shared memory.  The warps pull
+//                        tiles from the CTA's own list (an atomic counter in shared memory),
+//                        so a sub-partition that also hosts the producer / a consumer warp
+//                        simply takes fewer of them.
+//   warp  NR             producer: waits, in list order, for the tiles of its own CTA, turns
+//                        the tile's costs into weights relative to the CTA's running minimum
+//                        `ref` (online softmax: when a tile lowers ref, the weighted sums
+//                        gathered so far are rescaled by exp(-(ref_old-ref_new)/lambda)), and
+//                        issues one cp.async.bulk.tensor.2d per [40 rows x 128 samples] box.
+//   warps [NR+1, NR+5)   consumers: box (tile, chunk) belongs to warp chunk % 4, which has its
+//                        own ring of stages -- one waiter and one releaser per mbarrier, in
+//                        strict alternation with the producer (a shared ring would let a
+//                        fast warp run two phases ahead of a barrier, which parity waits
+//                        cannot tell apart) -- and the rows of a chunk are only ever touched
+//                        by their owner.  Half-warp h takes the rows of parity h, lane
+//                        q of it eight samples of the row; its partial of every row lives in
+//                        shared memory (s_part[row][16]) -- no shuffles in the steady state.
+// The tile list of a CTA is a static function of the tile index (tile = i * gridDim + cta) and
+// the producer consumes it in list order whichever warp computed a tile, so every CTA's sums
+// are formed in the same order on every run: results are bitwise reproducible.  At the end
+// each CTA writes {ref, eta, row sums} to a record; the last CTA (ticket) merges the records
+// in CTA order, rescaling each by exp(-(ref_c-beta)/lambda), converts to the fixed-point
+// accumulators and applies the U update (part 5).
 //
 // Registers: the CTA is launched with 96 per thread (640 threads); the consumer warpgroup
 // hands back all but 32 of its registers (setmaxnreg.dec) and the four warpgroups holding the
@@ -40,56 +49,71 @@
 #include "model.cuh"
 #include "philox.cuh"
 
+#include <stdlib.h>
+
 namespace mppi {
 
 constexpr int kStTileK     = 128;   // samples per rollout tile: one warp, four samples per lane
 constexpr int kStTileR     = 40;    // eps rows per TMA box
-constexpr int kStStages    = 6;     // boxes in flight per SM (6 x 20 KB)
+constexpr int kStMaxStages = 8;     // boxes in flight per SM (8 x 20 KB): two per consumer warp;
+                                    // 4 (one per consumer warp) when shared memory is short
 constexpr int kStConsumers = 4;     // consumer warps
-constexpr int kStRowsPerWarp = kStTileR / kStConsumers;
-
-struct StepStageHdr {
-    int   chunk;     // row box index of the tile in this stage; < 0: no more work
-    float scale;     // != 1: rescale the partial sums before adding this tile (chunk 0 only)
-    int   pad_[2];
-};
+constexpr int kStMergeGroups = 8;   // CTA groups of the final merge
 
 struct StepSmemLayout {
-    size_t tile, wt, part, u, hdr, bars, done, misc, total;
+    size_t tile, wt, part, u, scale, bars, done, misc, total;
 };
 
-__host__ __device__ inline StepSmemLayout step_smem_layout(int T, int A, int nr)
+__host__ __device__ inline StepSmemLayout step_smem_layout(int T, int A, long long list_len,
+                                                           int nstages)
 {
     const int R = T * A;
     const int nchunk = (R + kStTileR - 1) / kStTileR;
     StepSmemLayout l;
     size_t o = 0;
-    l.tile = o; o += (size_t)kStStages * kStTileR * kStTileK * sizeof(float);
-    l.wt   = o; o += (size_t)kStStages * kStTileK * sizeof(float);
-    l.part = o; o += (size_t)nchunk * kStTileR * 32 * sizeof(float);
-    l.u    = o; o += (size_t)T * 4 * A * sizeof(float);
-    l.hdr  = o; o += (size_t)kStStages * sizeof(StepStageHdr);
-    l.bars = o; o += (size_t)2 * kStStages * sizeof(uint64_t);
-    l.done = o; o += (size_t)((nr + 3) / 4 * 4) * sizeof(unsigned int);
-    l.misc = o; o += 16;
+    l.tile  = o; o += (size_t)nstages * kStTileR * kStTileK * sizeof(float);
+    l.wt    = o; o += (size_t)nstages * kStTileK * sizeof(float);
+    l.part  = o; o += (size_t)nchunk * kStTileR * 16 * sizeof(float);
+    l.u     = o; o += (size_t)T * 4 * A * sizeof(float);
+    l.scale = o; o += (size_t)kStMaxStages * sizeof(float);
+    l.bars  = o; o += (size_t)2 * kStMaxStages * sizeof(uint64_t);
+    l.done  = o; o += (size_t)((list_len + 3) / 4 * 4) * sizeof(unsigned int);
+    l.misc  = o; o += 32;
     l.total = o;
     return l;
 }
 
+// the merge of the per-CTA records reuses the tile ring: [groups][R+1] doubles + [grid] floats
+__host__ __device__ inline size_t step_merge_bytes(int R, int grid)
+{
+    return (size_t)kStMergeGroups * (R + 8) * sizeof(double) + (size_t)(grid + R) * sizeof(float) + 64;
+}
+
 #ifdef MPPI_STEP_TRACE
-// development aid: globaltimer stamps of CTA 0..3 -- [cta][0]: kernel start, [cta][1+w*8+round]:
-// rollout warp w finished round, [cta][200]: producer issued its last box, [cta][201]: consumers
-// done (after the CTA barrier), [cta][202]: record written, [cta][203]: finalize done
-__device__ unsigned long long g_step_trace[4][256];
 __device__ __forceinline__ unsigned long long gtimer()
 {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+// development aid (tools/step_trace.py): globaltimer stamps of CTA 0..3
+//   g_step_trace[cta][0] kernel start, [200] producer issued its last box, [201] consumers done,
+//   [202] record written, [0][203] finalize done
+//   g_step_trace_li[cta][0][li] rollout of list entry li complete, [1][li] producer starts on it,
+//   [2][li] producer has issued its last box
+__device__ unsigned long long g_step_trace[4][256];
+__device__ unsigned long long g_step_trace_li[4][3][128];
+// every CTA: [0] start, [1] last rollout warp done, [2] producer done, [3] consumers done,
+// [4] ticket taken; [0][5] merge begins (last CTA), [0][6] finalize done, [0][7] last CTA id
+__device__ unsigned long long g_step_trace_all[160][8];
+#define STEP_TRACE_ALL(slot) do { g_step_trace_all[blockIdx.x][slot] = gtimer(); } while (0)
 #define STEP_TRACE(slot) do { if (blockIdx.x < 4) g_step_trace[blockIdx.x][slot] = gtimer(); } while (0)
+#define STEP_TRACE_LI(j, li) \
+    do { if (blockIdx.x < 4 && (li) < 128) g_step_trace_li[blockIdx.x][j][li] = gtimer(); } while (0)
 #else
 #define STEP_TRACE(slot) do { } while (0)
+#define STEP_TRACE_ALL(slot) do { } while (0)
+#define STEP_TRACE_LI(j, li) do { } while (0)
 #endif
 
 template <uint32_t N> __device__ __forceinline__ void setmaxnreg_inc()
@@ -111,53 +135,55 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
             long long k_local, int T, const float *U,
             const ProblemDev *__restrict__ prob, float *__restrict__ S, CtlDev *__restrict__ ctl,
             unsigned long long k_offset, const __grid_constant__ SamplerParams sp,
-            float *__restrict__ part, long long *__restrict__ acc, FinalizeArgs fin)
+            float *__restrict__ part, long long *__restrict__ acc, FinalizeArgs fin,
+            int nstages)
 {
     static_assert((NR + 1) % 4 == 0, "rollout warps + producer must fill whole warpgroups");
     constexpr int kThreads = (NR + kStConsumers + 1) * 32;
     constexpr int kEpiThreads = (NR + 1) * 32;      // rollout + producer warps run the epilogue
     constexpr uint32_t kBoxBytes = kStTileR * kStTileK * sizeof(float);
+    constexpr int kBoxFloats = kStTileR * kStTileK;
     const int R = T * A;
     const int nchunk = (R + kStTileR - 1) / kStTileR;
 
     // declared 1024-byte aligned (TMA destinations need 128): no integer round-trip on the
     // address, so every access below stays a shared-space LDS/STS
     extern __shared__ __align__(1024) uint8_t base[];
-    const StepSmemLayout L = step_smem_layout(T, A, NR);
+    const long long ntiles = (long long)(ld / kStTileK);
+    const long long list_len = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // this CTA's tiles
+    const StepSmemLayout L = step_smem_layout(T, A, (ntiles + gridDim.x - 1) / gridDim.x, nstages);
     float *s_tile = reinterpret_cast<float *>(base + L.tile);          // [stage][40][128]
     float *s_wt   = reinterpret_cast<float *>(base + L.wt);            // [stage][128]
-    float *s_part = reinterpret_cast<float *>(base + L.part);          // [nchunk*40][32]
+    float *s_part = reinterpret_cast<float *>(base + L.part);          // [nchunk*40][16]
     float *s_u    = reinterpret_cast<float *>(base + L.u);             // [T][4A]
-    StepStageHdr *s_hdr = reinterpret_cast<StepStageHdr *>(base + L.hdr);
+    float *s_scale = reinterpret_cast<float *>(base + L.scale);        // [stage] rescale of the box's tile
     uint64_t *full_bar  = reinterpret_cast<uint64_t *>(base + L.bars);
-    uint64_t *empty_bar = full_bar + kStStages;
-    unsigned int *s_done = reinterpret_cast<unsigned int *>(base + L.done);   // [NR] rounds finished
-    float *s_misc = reinterpret_cast<float *>(base + L.misc);          // {ref, eta, last-CTA flag}
+    uint64_t *empty_bar = full_bar + kStMaxStages;
+    unsigned int *s_done = reinterpret_cast<unsigned int *>(base + L.done);   // [list] tile complete
+    float *s_misc = reinterpret_cast<float *>(base + L.misc);          // {ref, eta, last-CTA flag, next}
     int *s_last = reinterpret_cast<int *>(s_misc + 2);
+    unsigned int *s_next = reinterpret_cast<unsigned int *>(s_misc + 3);   // next list entry to roll out
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) STEP_TRACE(0);
+    if (threadIdx.x == 0) { STEP_TRACE(0); STEP_TRACE_ALL(0); }
 
     for (int i = threadIdx.x; i < R; i += kThreads) {
         const float u = U[i];
         const float ui = __fmul_rn(u, prob->inv_s[i % A]);            // src/cost.cu:46
         reinterpret_cast<float4 *>(s_u)[i] = make_float4(u, u, ui, ui);
     }
-    for (int i = threadIdx.x; i < nchunk * kStTileR * 32; i += kThreads) s_part[i] = 0.0f;
-    if (threadIdx.x < NR) s_done[threadIdx.x] = 0u;
+    for (int i = threadIdx.x; i < nchunk * kStTileR * 16; i += kThreads) s_part[i] = 0.0f;
+    for (int i = threadIdx.x; i < (int)list_len; i += kThreads) s_done[i] = 0u;
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < kStStages; ++s) {
+        *s_next = 0u;
+        for (int s = 0; s < nstages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kStConsumers);
+            mbar_init(&empty_bar[s], 1);
         }
         fence_mbar_init();
         fence_proxy_async();
     }
     __syncthreads();
-
-    const long long ntiles = (long long)(ld / kStTileK);
-    const long long nslots = (long long)NR * gridDim.x;
 
     if (warp <= NR) setmaxnreg_inc<112>();
     else            setmaxnreg_dec<32>();
@@ -168,9 +194,12 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
         m2.load(prob);
         const unsigned long long step = ctl->step;
         unsigned long long key = kMinKeyInit;
-        unsigned int round = 0;
-        for (long long tile = (long long)warp * gridDim.x + blockIdx.x; tile < ntiles;
-             tile += nslots) {
+        for (;;) {
+            unsigned int li = 0;
+            if (lane == 0) li = atomicAdd(s_next, 1u);
+            li = __shfl_sync(0xffffffffu, li, 0);
+            if ((long long)li >= list_len) break;
+            const long long tile = (long long)li * gridDim.x + blockIdx.x;
             const size_t g = (size_t)tile * 32 + lane;                 // this lane's Philox quad
             f2 x2[2][2 * A], c2[2];
 #pragma unroll
@@ -222,175 +251,207 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
             __threadfence();
             fence_proxy_async_all();
             __syncwarp();
-            ++round;
             if (lane == 0) {
-                st_release_cta_shared_u32(&s_done[warp], round);
-                STEP_TRACE(1 + warp * 8 + (round - 1));
+                st_release_cta_shared_u32(&s_done[li], 1u);
+                STEP_TRACE_LI(0, li);
             }
         }
         key = warp_min_u64(key);
         if (lane == 0 && key != kMinKeyInit) atomicMin(&ctl->min_key, key);
+#ifdef MPPI_STEP_TRACE
+        if (lane == 0) atomicMax(&g_step_trace_all[blockIdx.x][1], gtimer());
+#endif
     } else if (warp == NR) {
         // ================================ producer ===================================
         if (lane == 0) tma_prefetch_desc(&tmap_eps);
         const float nil = prob->neg_inv_lambda;
-        float ref = __int_as_float(0x7f800000);        // +inf: no sample seen yet
+        const float inf = __int_as_float(0x7f800000);
+        float ref = inf;                                // no sample seen yet
         float eta_part = 0.0f;                          // this lane's share of eta, relative to ref
-        int stage = 0;
-        uint32_t phase = 0;
-        for (unsigned int round = 0; (long long)round * nslots + blockIdx.x < ntiles; ++round) {
-            for (int w = 0; w < NR; ++w) {
-                const long long tile = (long long)round * nslots + (long long)w * gridDim.x + blockIdx.x;
-                if (tile >= ntiles) break;
-                if (lane == 0)
-                    while (ld_acquire_cta_shared_u32(&s_done[w]) < round + 1) __nanosleep(256);
+        const int depth = nstages / kStConsumers;       // ring depth of every consumer warp
+        for (long long li = 0; li < list_len; ++li) {
+            const long long tile = li * gridDim.x + blockIdx.x;
+            if (lane == 0)
+                while (ld_acquire_cta_shared_u32(&s_done[li]) == 0u) __nanosleep(256);
+            __syncwarp();
+            if (lane == 0) STEP_TRACE_LI(1, li);
+            // exp_red (src/point_mass.cu:518) for this lane's four samples of the tile
+            const long long k0 = tile * kStTileK + 4 * lane;
+            const float4 s4 = __ldcg(reinterpret_cast<const float4 *>(S + k0));
+            const bool v0 = k0 + 0 < k_local, v1 = k0 + 1 < k_local, v2 = k0 + 2 < k_local,
+                       v3 = k0 + 3 < k_local;
+            float tmin = fminf(fminf(v0 ? s4.x : inf, v1 ? s4.y : inf),
+                               fminf(v2 ? s4.z : inf, v3 ? s4.w : inf));
+            tmin = warp_min_f(tmin);
+            float scale = 1.0f;
+            if (tmin < ref) {
+                scale = expf(__fmul_rn(nil, __fsub_rn(ref, tmin)));   // ref = +inf -> 0
+                eta_part *= scale;
+                ref = tmin;
+            }
+            float4 w4;
+            w4.x = v0 ? expf(__fmul_rn(nil, __fsub_rn(s4.x, ref))) : 0.0f;
+            w4.y = v1 ? expf(__fmul_rn(nil, __fsub_rn(s4.y, ref))) : 0.0f;
+            w4.z = v2 ? expf(__fmul_rn(nil, __fsub_rn(s4.z, ref))) : 0.0f;
+            w4.w = v3 ? expf(__fmul_rn(nil, __fsub_rn(s4.w, ref))) : 0.0f;
+            eta_part += (w4.x + w4.y) + (w4.z + w4.w);
+            // newest rows first: the last time steps of the tile were written a few microseconds
+            // ago and are still in L2, the first ones ~a tile time ago and are long evicted
+            for (int chunk = nchunk - 1; chunk >= 0; --chunk) {
+                // k-th box of its owner -> slot k % depth of the owner's ring
+                const int cw = chunk & (kStConsumers - 1);
+                const int own = (nchunk - cw + kStConsumers - 1) / kStConsumers;   // owner's boxes per tile
+                const long long k = li * own + (own - 1 - (chunk >> 2));
+                const int stage = cw + kStConsumers * (int)(k % depth);
+                const uint32_t phase = (uint32_t)((k / depth) & 1);
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                *reinterpret_cast<float4 *>(s_wt + stage * kStTileK + 4 * lane) = w4;
+                if (lane == 0) s_scale[stage] = scale;
                 __syncwarp();
-                // exp_red (src/point_mass.cu:518) for this lane's four samples of the tile
-                const long long k0 = tile * kStTileK + 4 * lane;
-                const float4 s4 = __ldcg(reinterpret_cast<const float4 *>(S + k0));
-                const bool v0 = k0 + 0 < k_local, v1 = k0 + 1 < k_local, v2 = k0 + 2 < k_local,
-                           v3 = k0 + 3 < k_local;
-                const float inf = __int_as_float(0x7f800000);
-                float tmin = fminf(fminf(v0 ? s4.x : inf, v1 ? s4.y : inf),
-                                   fminf(v2 ? s4.z : inf, v3 ? s4.w : inf));
-                tmin = warp_min_f(tmin);
-                float scale = 1.0f;
-                if (tmin < ref) {
-                    scale = expf(__fmul_rn(nil, __fsub_rn(ref, tmin)));   // ref = +inf -> 0
-                    eta_part *= scale;
-                    ref = tmin;
-                }
-                float4 w4;
-                w4.x = v0 ? expf(__fmul_rn(nil, __fsub_rn(s4.x, ref))) : 0.0f;
-                w4.y = v1 ? expf(__fmul_rn(nil, __fsub_rn(s4.y, ref))) : 0.0f;
-                w4.z = v2 ? expf(__fmul_rn(nil, __fsub_rn(s4.z, ref))) : 0.0f;
-                w4.w = v3 ? expf(__fmul_rn(nil, __fsub_rn(s4.w, ref))) : 0.0f;
-                eta_part += (w4.x + w4.y) + (w4.z + w4.w);
-                for (int chunk = 0; chunk < nchunk; ++chunk) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    *reinterpret_cast<float4 *>(s_wt + stage * kStTileK + 4 * lane) = w4;
-                    if (lane == 0) {
-                        s_hdr[stage].chunk = chunk;
-                        s_hdr[stage].scale = chunk == 0 ? scale : 1.0f;
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(&full_bar[stage], kBoxBytes);
-                        tma_load_2d(s_tile + (size_t)stage * kStTileR * kStTileK, &tmap_eps,
-                                    (int)(tile * kStTileK), chunk * kStTileR, &full_bar[stage]);
-                    }
-                    if (++stage == kStStages) { stage = 0; phase ^= 1; }
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full_bar[stage], kBoxBytes);
+                    tma_load_2d(s_tile + (size_t)stage * kBoxFloats, &tmap_eps,
+                                (int)(tile * kStTileK), chunk * kStTileR, &full_bar[stage]);
                 }
             }
+            if (lane == 0) STEP_TRACE_LI(2, li);
         }
-        // no more tiles: release the consumers
-        if (lane == 0) STEP_TRACE(200);
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (lane == 0) {
-            s_hdr[stage].chunk = -1;
-            s_hdr[stage].scale = 1.0f;
-            mbar_arrive(&full_bar[stage]);
-        }
+        if (lane == 0) { STEP_TRACE(200); STEP_TRACE_ALL(2); }
         eta_part = warp_sum(eta_part);
         if (lane == 0) { s_misc[0] = ref; s_misc[1] = eta_part; }
     } else {
         // ================================ consumers ==================================
+        // this warp owns the boxes with chunk % 4 == cw; its k-th box sits in slot k % depth of
+        // its own ring (stages cw, cw+4, ...)
         const int cw = warp - (NR + 1);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (;;) {
-            mbar_wait(&full_bar[stage], phase);
-            const int chunk = s_hdr[stage].chunk;
-            const float scale = s_hdr[stage].scale;
-            if (chunk < 0) break;
-            if (scale != 1.0f) {
-                // a new minimum: everything gathered so far is relative to the old one
-                for (int cc = 0; cc < nchunk; ++cc)
-#pragma unroll
-                    for (int rr = 0; rr < kStRowsPerWarp; ++rr) {
-                        float *p = s_part + (size_t)(cc * kStTileR + cw + kStConsumers * rr) * 32 + lane;
-                        *p = *p * scale;
+        const int h = lane >> 4, q = lane & 15;
+        const int depth = nstages / kStConsumers;
+        const int own = nchunk > cw ? (nchunk - cw + kStConsumers - 1) / kStConsumers : 0;
+        long long k = 0;
+        for (long long li = 0; li < list_len; ++li) {
+            for (int chunk = cw + kStConsumers * (own - 1); chunk >= 0; chunk -= kStConsumers, ++k) {
+                const int stage = cw + kStConsumers * (int)(k % depth);
+                const uint32_t phase = (uint32_t)((k / depth) & 1);
+                mbar_wait(&full_bar[stage], phase);
+                if (chunk == cw + kStConsumers * (own - 1)) {
+                    // first box of this tile for this warp: a new minimum rescales everything
+                    // this warp has gathered so far (the rows of all its chunks)
+                    const float scale = s_scale[stage];
+                    if (scale != 1.0f) {
+                        for (int cc = cw; cc < nchunk; cc += kStConsumers) {
+                            float *p = s_part + (size_t)cc * kStTileR * 16 + lane;
+#pragma unroll 4
+                            for (int i = 0; i < kStTileR / 2; ++i) p[i * 32] *= scale;
+                        }
                     }
+                }
+                const float *wt = s_wt + stage * kStTileK + 4 * q;
+                const float4 w0 = *reinterpret_cast<const float4 *>(wt);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wt + 64);
+                // half-warp h: rows h, h+2, ...; lane q: samples 4q..4q+3 and 64+4q..64+4q+3
+                const float *tile = s_tile + (size_t)stage * kBoxFloats + (size_t)h * kStTileK + 4 * q;
+                float *pp = s_part + (size_t)chunk * kStTileR * 16 + lane;     // [(2j+h)*16 + q]
+#pragma unroll 2
+                for (int j = 0; j < kStTileR / 2; ++j) {
+                    const float4 e0 = *reinterpret_cast<const float4 *>(tile + (size_t)j * 2 * kStTileK);
+                    const float4 e1 = *reinterpret_cast<const float4 *>(tile + (size_t)j * 2 * kStTileK + 64);
+                    float a = pp[j * 32];
+                    a = fmaf(e0.x, w0.x, a);
+                    a = fmaf(e0.y, w0.y, a);
+                    a = fmaf(e0.z, w0.z, a);
+                    a = fmaf(e0.w, w0.w, a);
+                    a = fmaf(e1.x, w1.x, a);
+                    a = fmaf(e1.y, w1.y, a);
+                    a = fmaf(e1.z, w1.z, a);
+                    a = fmaf(e1.w, w1.w, a);
+                    pp[j * 32] = a;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
             }
-            const float4 w4 = *reinterpret_cast<const float4 *>(s_wt + stage * kStTileK + 4 * lane);
-            const float *tile = s_tile + (size_t)stage * kStTileR * kStTileK + 4 * lane;
-            float *pp = s_part + (size_t)(chunk * kStTileR + cw) * 32 + lane;
-            // two batches of rows: the consumer warps live on 32 registers
-            constexpr int kHalf = kStRowsPerWarp / 2;
-#pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-                float a_[kHalf];
-                float4 e_[kHalf];
-#pragma unroll
-                for (int i = 0; i < kHalf; ++i) {
-                    const int rr = hb * kHalf + i;
-                    e_[i] = *reinterpret_cast<const float4 *>(tile + (size_t)(cw + kStConsumers * rr) * kStTileK);
-                    a_[i] = pp[(size_t)rr * kStConsumers * 32];
-                }
-                if (hb == 1) {
-                    // every read of the stage's box is in registers: hand the slot back early
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[stage]);
-                }
-#pragma unroll
-                for (int i = 0; i < kHalf; ++i) {
-                    const int rr = hb * kHalf + i;
-                    float a = a_[i];
-                    a = fmaf(e_[i].x, w4.x, a);
-                    a = fmaf(e_[i].y, w4.y, a);
-                    a = fmaf(e_[i].z, w4.z, a);
-                    a = fmaf(e_[i].w, w4.w, a);
-                    pp[(size_t)rr * kStConsumers * 32] = a;
-                }
-            }
-            if (++stage == kStStages) { stage = 0; phase ^= 1; }
         }
     }
     __syncthreads();
     if (warp > NR) return;                 // consumers are done; the other warps finish the step
-    if (threadIdx.x == 0) STEP_TRACE(201);
+    if (threadIdx.x == 0) { STEP_TRACE(201); STEP_TRACE_ALL(3); }
 
-    // ---- this CTA's record: {ref, eta, row sums}, all relative to ref
-    float *rec = part + (size_t)blockIdx.x * (R + 2);
-    for (int r = warp; r < R; r += kEpiThreads / 32) {
-        const float v = warp_sum(s_part[(size_t)r * 32 + lane]);
-        if (lane == 0) rec[2 + r] = v;
+    // ---- this CTA's record: {row sums [R], eta, ref}, all relative to ref; the stride is a
+    //      multiple of four floats so that the merge reads float4 columns
+    const int rstride = (R + 2 + 3) & ~3;
+    float *rec = part + (size_t)blockIdx.x * rstride;
+    for (int rb = 2 * warp; rb < R; rb += 2 * (kEpiThreads / 32)) {      // two rows per warp pass
+        const int r = rb + (lane >> 4);
+        float v = r < R ? s_part[(size_t)r * 16 + (lane & 15)] : 0.0f;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((lane & 15) == 0 && r < R) rec[r] = v;
     }
-    if (threadIdx.x == 0) { rec[0] = s_misc[0]; rec[1] = s_misc[1]; }
+    if (threadIdx.x == 0) { rec[R] = s_misc[1]; rec[R + 1] = s_misc[0]; }
 
     __threadfence();                       // the record and the min key before the ticket
     named_bar_sync(1, kEpiThreads);
     if (threadIdx.x == 0) {
         STEP_TRACE(202);
+        STEP_TRACE_ALL(4);
         const unsigned ticket = atomicAdd(&ctl->done, 1u);
         *s_last = (ticket == gridDim.x - 1);
     }
     named_bar_sync(1, kEpiThreads);
     if (*s_last) {
-        // ---- merge the records in CTA order (deterministic), then part 5
+        // ---- merge the records (fixed order: CTA groups, then CTAs inside a group), then part 5
         __threadfence();
+#ifdef MPPI_STEP_TRACE
+        if (threadIdx.x == 0) { g_step_trace_all[0][5] = gtimer(); g_step_trace_all[0][7] = blockIdx.x; }
+#endif
         const float nil = prob->neg_inv_lambda;
         const unsigned long long mk = *reinterpret_cast<volatile unsigned long long *>(&ctl->min_key);
         const float beta = ordered_to_float((uint32_t)(mk >> 32));
-        float *s_f = s_tile;                                           // [gridDim.x]
-        for (int c = threadIdx.x; c < (int)gridDim.x; c += kEpiThreads) {
-            const float ref_c = __ldcg(part + (size_t)c * (R + 2));
+        const int nc = (int)gridDim.x;
+        const int ncol = rstride / 4;                                   // float4 columns of a record
+        double *s_m = reinterpret_cast<double *>(base + L.tile);        // [groups][rstride]
+        float *s_f = reinterpret_cast<float *>(s_m + (size_t)kStMergeGroups * rstride);   // [grid]
+        float *s_unew = s_f + nc;                                       // [R]
+        for (int c = threadIdx.x; c < nc; c += kEpiThreads) {
+            const float ref_c = __ldcg(part + (size_t)c * rstride + R + 1);
             s_f[c] = expf(__fmul_rn(nil, __fsub_rn(ref_c, beta)));     // ref_c = +inf -> 0
         }
         named_bar_sync(1, kEpiThreads);
-        for (int i = threadIdx.x; i <= R; i += kEpiThreads) {
-            const size_t off = i < R ? 2 + (size_t)i : 1;               // i == R: eta
+        const int per = (nc + kStMergeGroups - 1) / kStMergeGroups;
+        for (int it = threadIdx.x; it < kStMergeGroups * ncol; it += kEpiThreads) {
+            const int gq = it / ncol, col = it - gq * ncol;
+            const float4 *src = reinterpret_cast<const float4 *>(part) + col;
+            const int c0 = gq * per, c1 = min(nc, c0 + per);
+            double sx = 0.0, sy = 0.0, sz = 0.0, sw = 0.0;
+            for (int cb = c0; cb < c1; cb += 5) {                       // 5 x 16 B in flight, fixed order
+                float4 v[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                    v[j] = cb + j < c1 ? __ldcg(src + (size_t)(cb + j) * ncol)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                    if (cb + j < c1) {
+                        const double f = (double)s_f[cb + j];
+                        sx += (double)v[j].x * f; sy += (double)v[j].y * f;
+                        sz += (double)v[j].z * f; sw += (double)v[j].w * f;
+                    }
+            }
+            double *dst = s_m + (size_t)gq * rstride + 4 * col;
+            dst[0] = sx; dst[1] = sy; dst[2] = sz; dst[3] = sw;
+        }
+        named_bar_sync(1, kEpiThreads);
+        for (int i = threadIdx.x; i <= R; i += kEpiThreads) {           // i == R: eta
             double s = 0.0;
-            for (int c = 0; c < (int)gridDim.x; ++c)
-                s += (double)__ldcg(part + (size_t)c * (R + 2) + off) * (double)s_f[c];
+#pragma unroll
+            for (int gq = 0; gq < kStMergeGroups; ++gq) s += s_m[(size_t)gq * rstride + i];
             acc[i] = __double2ll_rn(s * kAccScale);
         }
         __threadfence();
         named_bar_sync(1, kEpiThreads);
         finalize_body(acc, fin.U, fin.U_prev, prob, ctl, fin.next_act, fin.T, fin.A, fin.flags,
-                      s_tile + 1024, kEpiThreads, 1);
+                      s_unew, kEpiThreads, 1);
 #ifdef MPPI_STEP_TRACE
-        if (threadIdx.x == 0) g_step_trace[0][203] = gtimer();
+        if (threadIdx.x == 0) { g_step_trace[0][203] = gtimer(); g_step_trace_all[0][6] = gtimer(); }
 #endif
     }
 }
@@ -400,6 +461,19 @@ extern "C" int mppi_debug_read_step_trace(unsigned long long *out)
 {
     return (int)cudaMemcpyFromSymbol(out, g_step_trace, sizeof(g_step_trace));
 }
+extern "C" int mppi_debug_read_step_trace_all(unsigned long long *out, int clear)
+{
+    int rc = (int)cudaMemcpyFromSymbol(out, g_step_trace_all, sizeof(g_step_trace_all));
+    if (clear) {
+        static unsigned long long zeros[160][8];
+        rc |= (int)cudaMemcpyToSymbol(g_step_trace_all, zeros, sizeof(zeros));
+    }
+    return rc;
+}
+extern "C" int mppi_debug_read_step_trace_li(unsigned long long *out)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_step_trace_li, sizeof(g_step_trace_li));
+}
 #endif
 
 // =================================================================================
@@ -407,18 +481,52 @@ extern "C" int mppi_debug_read_step_trace(unsigned long long *out)
 // =================================================================================
 namespace {
 constexpr int kStepNR = 15;   // rollout warps per CTA (+ 1 producer = 4 warpgroups)
+constexpr size_t kStepSmemMax = 227 * 1024;
+
+struct StepGeom {
+    long long ntiles, list_len;
+    int grid, nstages;
+    size_t smem;
+};
+
+// grid, tile-list length and the deepest TMA ring that fits next to the row sums
+StepGeom step_geom(int T, int A, long long k_pad, int num_sms)
+{
+    StepGeom g{};
+    g.ntiles = k_pad / kStTileK;
+    g.grid = (int)(g.ntiles < num_sms ? g.ntiles : num_sms);
+    g.list_len = (g.ntiles + g.grid - 1) / g.grid;
+    g.nstages = 0;
+    for (int ns = kStMaxStages; ns >= kStConsumers; ns -= kStConsumers) {
+        const size_t b = step_smem_layout(T, A, g.list_len, ns).total;
+        if (b <= kStepSmemMax &&
+            step_merge_bytes(T * A, g.grid) <= (size_t)ns * kStTileR * kStTileK * sizeof(float)) {
+            g.nstages = ns;
+            g.smem = b;
+            break;
+        }
+    }
+    if (const char *env = getenv("MPPI_STEP_STAGES")) {
+        const int v = atoi(env);
+        if (v >= kStConsumers && v % kStConsumers == 0 && v <= g.nstages &&
+            step_merge_bytes(T * A, g.grid) <= (size_t)v * kStTileR * kStTileK * sizeof(float)) {
+            g.nstages = v;
+            g.smem = step_smem_layout(T, A, g.list_len, v).total;
+        }
+    }
+    return g;
+}
 
 template <int A, bool STRICT>
 cudaError_t launch_step_t(const LaunchCtx &c, const CUtensorMap &tmap, float *eps, float *U,
                           const ProblemDev *prob, float *S, CtlDev *ctl, float *part,
                           long long *acc, const FinalizeArgs &fin)
 {
-    const size_t smem = step_smem_layout(c.horizon, c.act_dim, kStepNR).total;
-    const long long ntiles = c.k_pad / kStTileK;
-    const int grid = (int)(ntiles < c.num_sms ? ntiles : c.num_sms);
-    step_kernel<A, STRICT, kStepNR><<<grid, (kStepNR + kStConsumers + 1) * 32, smem, c.stream>>>(
+    const StepGeom g = step_geom(c.horizon, c.act_dim, c.k_pad, c.num_sms);
+    if (g.nstages == 0) return cudaErrorInvalidConfiguration;
+    step_kernel<A, STRICT, kStepNR><<<g.grid, (kStepNR + kStConsumers + 1) * 32, g.smem, c.stream>>>(
         tmap, eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U, prob, S, ctl,
-        (unsigned long long)c.k_offset, c.sampler, part, acc, fin);
+        (unsigned long long)c.k_offset, c.sampler, part, acc, fin, g.nstages);
     return cudaGetLastError();
 }
 
@@ -433,22 +541,25 @@ cudaError_t configure_step_a(int smem)
 }
 }  // namespace
 
-bool step_kernel_supported(int T, int A)
+bool step_kernel_supported(int T, int A, long long k_pad, int num_sms)
 {
-    return step_smem_layout(T, A, kStepNR).total <= 227 * 1024;
+    return step_geom(T, A, k_pad, num_sms).nstages >= kStConsumers;
 }
 
-size_t step_part_floats(const LaunchCtx &c) { return (size_t)c.num_sms * ((size_t)c.rows + 2); }
+size_t step_part_floats(const LaunchCtx &c)
+{
+    return (size_t)c.num_sms * (((size_t)c.rows + 2 + 3) & ~(size_t)3);
+}
 
 cudaError_t configure_step(const LaunchCtx &c)
 {
-    if (!step_kernel_supported(c.horizon, c.act_dim)) return cudaSuccess;
-    const int smem = (int)step_smem_layout(c.horizon, c.act_dim, kStepNR).total;
+    const StepGeom g = step_geom(c.horizon, c.act_dim, c.k_pad, c.num_sms);
+    if (g.nstages == 0) return cudaSuccess;
     switch (c.act_dim) {
-        case 1: return configure_step_a<1>(smem);
-        case 2: return configure_step_a<2>(smem);
-        case 3: return configure_step_a<3>(smem);
-        case 4: return configure_step_a<4>(smem);
+        case 1: return configure_step_a<1>((int)kStepSmemMax);
+        case 2: return configure_step_a<2>((int)kStepSmemMax);
+        case 3: return configure_step_a<3>((int)kStepSmemMax);
+        case 4: return configure_step_a<4>((int)kStepSmemMax);
         default: return cudaErrorInvalidValue;
     }
 }
