@@ -12,10 +12,14 @@ Printed JSON line (rank 0):
                in HBM, CUDA events on the controller's stream, max over ranks
   e2e          the same metric through the reference-facing call sequence with HOST buffers:
                set_x(x_host) ; get_act(next_act_host) per step (blocking), wall clock
-  roofline     the weighted-average kernel (part 4): algorithmic bytes / CUDA-event duration,
-               against MEASURED_PEAKS.json hbm_gbs
+  roofline     the dominant kernel: algorithmic bytes / CUDA-event duration against
+               MEASURED_PEAKS.json hbm_gbs.  With >= 4e5 samples on one GPU the whole step is ONE
+               kernel (step_kernel: 4KTA written + 4KTA read back + 8K); otherwise the
+               weighted-average kernel (part 4) of the kernel chain
   kernels      per-kernel average durations of the same chain (CUDA events between kernels,
                second timed region, direct launches instead of the graph)
+  other_chains the same workload through the kernel chains (fused two-kernel, unfused
+               three-kernel) with their per-kernel times and HBM fractions
   cpu_baseline the reference's own model/cost code (oracle/_ref) + oracle port of the
                reductions, 1 core, on a bounded sample of the workload
 `--impl reference` times that CPU path with all host threads instead.
@@ -199,12 +203,19 @@ def run_ours(args, name, K, T, A, dt, goal, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # chain selection: with >= 4e5 samples per GPU the fused sample+rollout kernel (one pass
-    # writes eps and integrates; identical eps values) beats the separate sampling kernel;
-    # below that the step is latency-bound and the 4-part chain with the TMA rollout wins.
+    # chain selection: with >= 4e5 samples per GPU the sampling is fused into the rollout (one
+    # pass writes eps and integrates; identical eps values) -- on a single shard as the
+    # one-kernel step, where the weighted average of finished tiles overlaps the rollout of
+    # the next ones; below that the step is latency-bound and the unfused chain with the TMA
+    # rollout wins.
     k_loc = capi.shard_range(K, rank, world)
     k_loc = k_loc[1] - k_loc[0]
-    flags = args.flags if args.flags >= 0 else (capi.FLAG_FUSED_SAMPLING if k_loc >= 400000 else 0)
+    if args.flags >= 0:
+        flags = args.flags
+    elif k_loc >= 400000:
+        flags = capi.FLAG_STEP_KERNEL if world == 1 else capi.FLAG_FUSED_SAMPLING
+    else:
+        flags = 0
     if world > 1:
         from mppi_gpu_b200.torch_dist import sharded_controller
         ctl = sharded_controller(K, T, dt, 2 * A, A, comm=args.comm, device=local_rank, seed=0,
@@ -265,8 +276,17 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     clk = clocks.stop() if rank == 0 else None
 
     k_local = ctl.k_local
+    one_kernel = bool(flags & capi.FLAG_STEP_KERNEL) and launches == args.steps
     avg_ms = max_over_ranks(kernels["average"])
-    alg_bytes = 4.0 * k_local * T * A + 4.0 * k_local
+    if one_kernel:
+        # eps written once and read back once, S written and read once.  The step IS this one
+        # kernel, so its average launch duration is taken from region 1 (K launches back to
+        # back between two CUDA events; includes the 20-byte D2H node) rather than from region
+        # 3, whose per-launch event pairs add the launch gap.
+        alg_bytes = 8.0 * k_local * T * A + 8.0 * k_local
+        avg_ms = ms_step
+    else:
+        alg_bytes = 4.0 * k_local * T * A + 4.0 * k_local
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -276,11 +296,14 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     ncu_traffic = None
     try:
-        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "average_traffic.json"))).get(
+        ncu_traffic = json.load(open(os.path.join(
+            ROOT, "profiles", "step_traffic.json" if one_kernel else "average_traffic.json"))).get(
             "dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "average_kernel (part 4: sum_k w_k eps_k[t,a])", "bound": "hbm",
+    roofline = {"kernel": ("step_kernel (parts 1-5 in one persistent kernel: eps written by the rollout "
+                           "warps, read back by the TMA-fed average warps)" if one_kernel else
+                           "average_kernel (part 4: sum_k w_k eps_k[t,a])"), "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
@@ -303,7 +326,9 @@ def run_ours(args, name, K, T, A, dt, goal, w):
                          % (eps_bytes / 1e6) if eps_bytes > 200e6 else
                          "working set fits L2 (%.0f MB eps): latency-bound config, no flush" % (eps_bytes / 1e6),
                    "flags": flags, "graph": not (flags & capi.FLAG_NO_GRAPH),
-                   "chain": ("sample+rollout(fused) -> weights -> average -> finalize"
+                   "chain": ("one kernel: sample+rollout warps || weights+average warps -> merge+finalize"
+                             if one_kernel else
+                             "sample+rollout(fused) -> weights -> average -> finalize"
                              if flags & capi.FLAG_FUSED_SAMPLING else
                              "sample -> rollout -> weights -> average -> finalize"),
                    "timing": "value: CUDA events on the controller stream around K graph launches; "
@@ -317,31 +342,42 @@ def run_ours(args, name, K, T, A, dt, goal, w):
         "kernels": per_kernel,
         "clocks": clk,
     }
-    if flags & capi.FLAG_FUSED_SAMPLING:
-        # the canonical 4-part chain (separate sampling kernel) timed beside it, same workload
+    if one_kernel:
+        per_kernel = {"step": {"ms": avg_ms, "hbm_gbs": achieved, "hbm_frac": achieved / peak,
+                               "ms_with_event_pairs": kernels["average"]}}
+        out["kernels"] = per_kernel
+    if world == 1 and flags & (capi.FLAG_FUSED_SAMPLING | capi.FLAG_STEP_KERNEL):
+        # the kernel chains timed beside it on the same workload: fused (sample+rollout, average)
+        # and the canonical unfused one (sample, rollout, average)
         ctl.close()
-        ctl = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=flags & ~capi.FLAG_FUSED_SAMPLING,
-                               device=local_rank) if world == 1 else None
-        if ctl is not None:
-            ctl.memcpy_set_data(x0, np.zeros((T, A), np.float32), goal, w)
+        ctl = None
+        base = flags & ~(capi.FLAG_FUSED_SAMPLING | capi.FLAG_STEP_KERNEL)
+        others = {}
+        for cname, cflags in (("fused_2_kernels", base | capi.FLAG_FUSED_SAMPLING), ("unfused_3_kernels", base)):
+            if cflags == flags:
+                continue
+            c2 = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=cflags, device=local_rank)
+            c2.memcpy_set_data(x0, np.zeros((T, A), np.float32), goal, w)
             for _ in range(3):
-                ctl.get_act()
-            ctl.timer_start()
+                c2.get_act()
+            c2.timer_start()
             for _ in range(args.steps):
-                ctl.step_enqueue()
-            ms4 = ctl.timer_stop() / args.steps
-            ctl.step_wait()
-            ctl.set_profiling(True)
+                c2.step_enqueue()
+            ms4 = c2.timer_stop() / args.steps
+            c2.step_wait()
+            c2.set_profiling(True)
             for _ in range(args.steps):
-                ctl.get_act()
-            kt4 = {k: ms / n for k, (ms, n) in ctl.kernel_times().items() if n}
-            ctl.set_profiling(False)
-            out["unfused_4part_chain"] = {
+                c2.get_act()
+            kt4 = {k: ms / n for k, (ms, n) in c2.kernel_times().items() if n}
+            c2.set_profiling(False)
+            c2.close()
+            others[cname] = {
                 "ms_per_step": ms4, "value": K * T / (ms4 * 1e-3),
                 "kernels": {k: ({"ms": v, "hbm_gbs": eps_bytes / (v * 1e-3) / 1e9,
                                  "hbm_frac": eps_bytes / (v * 1e-3) / 1e9 / peak}
                                 if k in ("sample", "rollout", "average") else {"ms": v})
                             for k, v in kt4.items()}}
+        out["other_chains"] = others
     if world > 1:
         out["collectives_ms"] = {
             "kind": "NVLink peer mailboxes (direct P2P stores + flags), sum fused with the U update"
@@ -383,7 +419,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--flags", type=int, default=-1,
-                    help="MPPI_FLAG_* bits; default: fused sampling (32) when >= 4e5 samples/GPU")
+                    help="MPPI_FLAG_* bits; default with >= 4e5 samples/GPU: the one-kernel step (128) "
+                         "on one GPU, fused sampling (32) on K-shards")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="K-shard exchange for --gpus > 1: NVLink peer mailboxes or NCCL")
