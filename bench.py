@@ -213,7 +213,8 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     if args.flags >= 0:
         flags = args.flags
     elif k_loc >= 400000:
-        flags = capi.FLAG_STEP_KERNEL if world == 1 else capi.FLAG_FUSED_SAMPLING
+        # (K-shards: the one-kernel step needs the single-exchange peer-mailbox merge)
+        flags = capi.FLAG_STEP_KERNEL if (world == 1 or args.comm == "p2p") else capi.FLAG_FUSED_SAMPLING
     else:
         flags = 0
     if world > 1:
@@ -276,7 +277,7 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     clk = clocks.stop() if rank == 0 else None
 
     k_local = ctl.k_local
-    one_kernel = bool(flags & capi.FLAG_STEP_KERNEL) and launches == args.steps
+    one_kernel = bool(flags & capi.FLAG_STEP_KERNEL) and launches == args.steps * (1 if world == 1 else 2)
     avg_ms = max_over_ranks(kernels["average"])
     if one_kernel:
         # eps written once and read back once, S written and read once.  The step IS this one
@@ -284,7 +285,8 @@ def run_ours(args, name, K, T, A, dt, goal, w):
         # back between two CUDA events; includes the 20-byte D2H node) rather than from region
         # 3, whose per-launch event pairs add the launch gap.
         alg_bytes = 8.0 * k_local * T * A + 8.0 * k_local
-        avg_ms = ms_step
+        if world == 1:
+            avg_ms = ms_step
     else:
         alg_bytes = 4.0 * k_local * T * A + 4.0 * k_local
     peaks = {}
@@ -379,11 +381,17 @@ def run_ours(args, name, K, T, A, dt, goal, w):
                             for k, v in kt4.items()}}
         out["other_chains"] = others
     if world > 1:
-        out["collectives_ms"] = {
-            "kind": "NVLink peer mailboxes (direct P2P stores + flags), sum fused with the U update"
-                    if args.comm == "p2p" else "ncclAllReduce inside the CUDA graph",
-            "min_u64": kernels.get("comm_min"),
-            "sum_i64" + ("+finalize" if args.comm == "p2p" else ""): kernels.get("comm_sum")}
+        if args.comm == "p2p":
+            out["collectives_ms"] = {
+                "kind": "ONE exchange per step over NVLink peer mailboxes (direct P2P stores + flags): "
+                        "every shard averages relative to its own minimum, the exchange kernel rescales "
+                        "by exp(-(beta_r-beta)/lambda), sums in rank order and applies the U update",
+                "min_u64": None,
+                "merge_i64+finalize": kernels.get("comm_sum")}
+        else:
+            out["collectives_ms"] = {
+                "kind": "ncclAllReduce(min) + ncclAllReduce(sum) inside the CUDA graph",
+                "min_u64": kernels.get("comm_min"), "sum_i64": kernels.get("comm_sum")}
         out["config"]["comm"] = args.comm
 
     # ---- CPU baseline beside it (rank 0, N=1 only): 1 core, bounded sample

@@ -82,7 +82,7 @@ struct mppi_handle {
     bool injected = false;
     bool profiling = false;
     bool pending = false;
-    bool prof_pending = false, prof_sampled = false;      // profiling times to collect at wait
+    bool prof_pending = false, prof_sampled = false, prof_one_kernel = false;      // profiling times to collect at wait
 
     cudaEvent_t ev[MPPI_K_COUNT + 1] = {};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -99,7 +99,7 @@ bool fused(const mppi_handle *h) { return (h->p.flags & MPPI_FLAG_FUSED_SAMPLING
 // the one-kernel step: sampled noise, single shard, row sums fit in shared memory
 bool one_kernel(const mppi_handle *h, bool sample)
 {
-    return sample && (h->p.flags & MPPI_FLAG_STEP_KERNEL) && !multi(h) &&
+    return sample && (h->p.flags & MPPI_FLAG_STEP_KERNEL) && (!multi(h) || p2p(h)) &&
            !(h->p.flags & MPPI_FLAG_SPLIT_KERNELS) && h->d_part != nullptr;
 }
 
@@ -140,8 +140,12 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
     if (one_kernel(h, sample)) {
         for (int i = 0; i < MPPI_K_AVERAGE; ++i) CK(mark());     // the time is booked on "average"
         CK(launch_step(c, h->tmap_st, h->d_eps, h->d_U, h->d_prob, h->d_S, h->d_ctl, h->d_part,
-                       h->d_acc, h->d_Uprev, h->d_next, h->p.flags));
+                       h->d_acc, h->d_Uprev, h->d_next, h->p.flags, !multi(h)));
         CK(mark());
+        if (p2p(h))
+            CK(launch_xchg_merge_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl,
+                                          h->d_next, h->p.flags, h->peer_mb, h->p.rank,
+                                          h->p.world_size));
         CK(mark());
         CK(cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * (kMaxAct + 1), cudaMemcpyDeviceToHost,
                            c.stream));
@@ -155,21 +159,27 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
     else
         CK(launch_rollout(c, h->d_eps, h->d_U, h->d_prob, h->d_S, h->d_ctl, sample && fused(h)));
     CK(mark());
-    if (p2p(h)) {
+    // peer-mailbox shards average relative to their own minimum and merge afterwards (one
+    // exchange); NCCL shards all-reduce beta first (two exchanges)
+    const bool split = (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) != 0;
+    const bool one_xchg = p2p(h) && !split;
+    if (p2p(h) && !one_xchg) {
         CK(launch_xchg_min(c, h->d_ctl, h->peer_mb, h->p.rank, h->p.world_size));
-    } else if (multi(h)) {
+    } else if (multi(h) && !p2p(h)) {
         if (!h->comm.allreduce_min_u64(&h->d_ctl->min_key, 1, c.stream, err))
             return fail(MPPI_ERR_COMM, "%s", err.c_str());
     }
     CK(mark());
-    const bool split = (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) != 0;
     if (split) CK(launch_weights(c, h->d_S, h->d_prob, h->d_ctl, h->d_wt, h->d_acc));
     CK(mark());
     const bool merge_fin = !split && !multi(h);
     CK(launch_average(c, h->tmap, split ? h->d_wt : h->d_S, h->d_acc, !split, merge_fin, h->d_prob,
                       h->d_ctl, h->d_U, h->d_Uprev, h->d_next, h->p.flags));
     CK(mark());
-    if (p2p(h)) {
+    if (one_xchg) {
+        CK(launch_xchg_merge_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
+                                      h->p.flags, h->peer_mb, h->p.rank, h->p.world_size));
+    } else if (p2p(h)) {
         // exchange + integer sum + U update in one kernel over peer memory
         CK(launch_xchg_sum_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
                                     h->p.flags, h->peer_mb, h->p.rank, h->p.world_size));
@@ -190,11 +200,11 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
 
 int kernels_per_step(const mppi_handle *h, bool sample)
 {
-    if (one_kernel(h, sample)) return 1;
+    if (one_kernel(h, sample)) return multi(h) ? 2 : 1;
     int n = 2;                                  // rollout, average(+weights,+finalize)
     if (sample && !fused(h)) n += 1;            // sampling
     if (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) n += 1;      // separate weights kernel
-    if (p2p(h)) n += 2;                         // xchg_min, xchg_sum+finalize
+    if (p2p(h)) n += (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) ? 2 : 1;   // (xchg_min,) xchg+finalize
     else if (multi(h) || (h->p.flags & MPPI_FLAG_SPLIT_KERNELS)) n += 1;   // finalize kernel
     return n;
 }
@@ -672,7 +682,7 @@ int mppi_step_enqueue(mppi_handle *h)
     if (h->profiling || (h->p.flags & MPPI_FLAG_NO_GRAPH)) {
         rc = enqueue_chain(h, sample, h->profiling ? h->ev : nullptr);
         if (rc) return rc;
-        if (h->profiling) { h->prof_pending = true; h->prof_sampled = sample; }
+        if (h->profiling) { h->prof_pending = true; h->prof_sampled = sample; h->prof_one_kernel = one_kernel(h, sample); }
     } else {
         if (!h->graph_exec[which] && (rc = build_graph(h, which)) != MPPI_OK) return rc;
         CK(cudaGraphLaunch(h->graph_exec[which], h->stream));
@@ -705,8 +715,10 @@ int mppi_step_wait(mppi_handle *h, float *next_act)
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
             const bool split = (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) != 0;
-            const bool ran = (i == MPPI_K_SAMPLE) ? (sample && !fused(h))
-                           : (i == MPPI_K_COMM_MIN || i == MPPI_K_COMM_SUM) ? multi(h)
+            const bool ran = h->prof_one_kernel ? (i == MPPI_K_AVERAGE || (i == MPPI_K_COMM_SUM && multi(h)))
+                           : (i == MPPI_K_SAMPLE) ? (sample && !fused(h))
+                           : (i == MPPI_K_COMM_MIN) ? (multi(h) && (!p2p(h) || split))
+                           : (i == MPPI_K_COMM_SUM) ? multi(h)
                            : (i == MPPI_K_WEIGHTS) ? split
                            : (i == MPPI_K_FINALIZE) ? ((split || multi(h)) && !p2p(h)) : true;
             if (ran) { h->ms_sum[i] += ms; h->launches[i] += 1; }

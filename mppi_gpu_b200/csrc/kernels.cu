@@ -710,6 +710,67 @@ xchg_sum_finalize_kernel(long long *__restrict__ acc, float *__restrict__ U,
     finalize_body(acc, U, U_prev, prob, ctl, next_act, T, A, flags, s_u);
 }
 
+// (3a+5'') ONE exchange per step: every shard has averaged with ITS OWN minimum beta_r as the
+// softmax reference (no beta exchange before the average), so acc_r = sum_k w~_k eps_k and
+// eta_r are relative to beta_r.  Each rank pushes {key_r, acc_r} to every peer, takes the
+// global minimum key, rescales every shard's accumulators by exp(-(beta_r - beta)/lambda) and
+// sums them in rank order -- the same arithmetic on the same bits on every rank, so the
+// replicated U stays bit-identical -- then applies the U update.  (The online-softmax merge
+// the one-kernel step uses between CTAs, applied between GPUs.)
+__global__ void __launch_bounds__(256)
+xchg_merge_finalize_kernel(long long *__restrict__ acc, float *__restrict__ U,
+                           float *__restrict__ U_prev, const ProblemDev *__restrict__ prob,
+                           CtlDev *__restrict__ ctl, float *__restrict__ next_act, int T, int A,
+                           unsigned flags, const __grid_constant__ PeerTable peers, int rank,
+                           int world, size_t slot_words)
+{
+    extern __shared__ float s_u[];
+    __shared__ double s_f[kMaxWorld];
+    const int R = T * A;
+    const unsigned long long seq = ctl->step + 1;
+    const unsigned long long mine = ctl->min_key;
+    for (int r = 0; r < world; ++r) {
+        unsigned long long *slot = peers.mb[r] + (size_t)rank * slot_words;
+        if (threadIdx.x == 0) st_relaxed_sys_u64(slot + 1, mine);
+        for (int i = threadIdx.x; i <= R; i += blockDim.x)
+            st_relaxed_sys_u64(slot + kMailboxHeaderWords + i, (unsigned long long)acc[i]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        st_release_sys_u64(peers.mb[threadIdx.x] + (size_t)rank * slot_words + 2, seq);
+        const unsigned long long *in = peers.mb[rank] + (size_t)threadIdx.x * slot_words;
+        if (!wait_seq(in + 2, seq)) atomicExch(&ctl->comm_error, 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long gkey = kMinKeyInit;
+        for (int r = 0; r < world; ++r) {
+            const unsigned long long k = ld_relaxed_sys_u64(peers.mb[rank] + (size_t)r * slot_words + 1);
+            gkey = k < gkey ? k : gkey;
+        }
+        const float beta = ordered_to_float((uint32_t)(gkey >> 32));
+        const float nil = prob->neg_inv_lambda;
+        for (int r = 0; r < world; ++r) {
+            const unsigned long long k = ld_relaxed_sys_u64(peers.mb[rank] + (size_t)r * slot_words + 1);
+            const float beta_r = ordered_to_float((uint32_t)(k >> 32));
+            s_f[r] = k == kMinKeyInit ? 0.0 : (double)expf(__fmul_rn(nil, __fsub_rn(beta_r, beta)));
+        }
+        ctl->min_key = gkey;                      // beta / argmin of the whole step
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= R; i += blockDim.x) {
+        double sum = 0.0;
+        for (int r = 0; r < world; ++r)
+            sum += (double)(long long)ld_relaxed_sys_u64(peers.mb[rank] + (size_t)r * slot_words +
+                                                         kMailboxHeaderWords + i) * s_f[r];
+        acc[i] = __double2ll_rn(sum);
+    }
+    __threadfence();
+    __syncthreads();
+    finalize_body(acc, U, U_prev, prob, ctl, next_act, T, A, flags, s_u);
+}
+
 // =================================================================================
 // layout conversion (parity taps): reference [K][R]  <->  internal [R][k_pad]
 // =================================================================================
@@ -998,6 +1059,20 @@ cudaError_t launch_xchg_sum_finalize(const LaunchCtx &c, long long *acc, float *
     return cudaGetLastError();
 }
 
+cudaError_t launch_xchg_merge_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
+                                       const ProblemDev *prob, CtlDev *ctl, float *next_act,
+                                       unsigned flags, unsigned long long *const *peer_mb, int rank,
+                                       int world)
+{
+    PeerTable pt{};
+    for (int r = 0; r < world; ++r) pt.mb[r] = peer_mb[r];
+    const size_t smem = sizeof(float) * (size_t)c.rows;
+    xchg_merge_finalize_kernel<<<1, 256, smem, c.stream>>>(acc, U, U_prev, prob, ctl, next_act,
+                                                           c.horizon, c.act_dim, flags, pt, rank,
+                                                           world, mailbox_slot_words(c.rows));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_to_internal(const LaunchCtx &c, const float *e_ref, float *eps)
 {
     dim3 grid((unsigned)((c.k_local + 31) / 32), (unsigned)((c.rows + 31) / 32));
@@ -1078,6 +1153,9 @@ cudaError_t configure_kernels(const LaunchCtx &c)
         e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(xchg_sum_finalize_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(xchg_merge_finalize_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
         if (e != cudaSuccess) return e;
     }

@@ -76,6 +76,13 @@ cudaError_t launch_xchg_sum_finalize(const LaunchCtx &c, long long *acc, float *
                                      unsigned flags, unsigned long long *const *peer_mb, int rank,
                                      int world);
 
+// the single exchange of the online-softmax K-shard merge: every shard averaged relative to
+// its own minimum; push {key, acc}, rescale by exp(-(beta_r-beta)/lambda), sum, U update
+cudaError_t launch_xchg_merge_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
+                                       const ProblemDev *prob, CtlDev *ctl, float *next_act,
+                                       unsigned flags, unsigned long long *const *peer_mb, int rank,
+                                       int world);
+
 // layout conversion between the reference's [K][T*A] and the internal K-minor [T*A][k_pad]
 cudaError_t launch_to_internal(const LaunchCtx &c, const float *e_ref, float *eps);
 cudaError_t launch_to_reference(const LaunchCtx &c, const float *eps, float *e_ref);
@@ -94,9 +101,11 @@ cudaError_t launch_trajectories(const LaunchCtx &c, const float *eps, const floa
 bool step_kernel_supported(int T, int A, long long k_pad, int num_sms);
 size_t step_part_floats(const LaunchCtx &c);
 cudaError_t configure_step(const LaunchCtx &c);
+//       finalize = false (K-shards): the last CTA stops after writing the fixed-point
+//       accumulators (relative to the shard's own minimum); launch_xchg_merge_finalize follows.
 cudaError_t launch_step(const LaunchCtx &c, const CUtensorMap &tmap, float *eps, float *U,
                         const ProblemDev *prob, float *S, CtlDev *ctl, float *part, long long *acc,
-                        float *U_prev, float *next_act, unsigned flags);
+                        float *U_prev, float *next_act, unsigned flags, bool finalize);
 constexpr int kStepTileK = 128, kStepTileR = 40;   // its TMA box
 
 // reset the control block (min key armed, step 0)

@@ -136,7 +136,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
             const ProblemDev *__restrict__ prob, float *__restrict__ S, CtlDev *__restrict__ ctl,
             unsigned long long k_offset, const __grid_constant__ SamplerParams sp,
             float *__restrict__ part, long long *__restrict__ acc, FinalizeArgs fin,
-            int nstages)
+            int nstages, int do_finalize)
 {
     static_assert((NR + 1) % 4 == 0, "rollout warps + producer must fill whole warpgroups");
     constexpr int kThreads = (NR + kStConsumers + 1) * 32;
@@ -446,6 +446,12 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
             for (int gq = 0; gq < kStMergeGroups; ++gq) s += s_m[(size_t)gq * rstride + i];
             acc[i] = __double2ll_rn(s * kAccScale);
         }
+        if (!do_finalize) {
+            // K-shard: the accumulators (relative to this shard's minimum, which stays in
+            // ctl->min_key) go through the cross-GPU merge kernel next
+            if (threadIdx.x == 0) ctl->done = 0;
+            return;
+        }
         __threadfence();
         named_bar_sync(1, kEpiThreads);
         finalize_body(acc, fin.U, fin.U_prev, prob, ctl, fin.next_act, fin.T, fin.A, fin.flags,
@@ -520,13 +526,13 @@ StepGeom step_geom(int T, int A, long long k_pad, int num_sms)
 template <int A, bool STRICT>
 cudaError_t launch_step_t(const LaunchCtx &c, const CUtensorMap &tmap, float *eps, float *U,
                           const ProblemDev *prob, float *S, CtlDev *ctl, float *part,
-                          long long *acc, const FinalizeArgs &fin)
+                          long long *acc, const FinalizeArgs &fin, bool finalize)
 {
     const StepGeom g = step_geom(c.horizon, c.act_dim, c.k_pad, c.num_sms);
     if (g.nstages == 0) return cudaErrorInvalidConfiguration;
     step_kernel<A, STRICT, kStepNR><<<g.grid, (kStepNR + kStConsumers + 1) * 32, g.smem, c.stream>>>(
         tmap, eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U, prob, S, ctl,
-        (unsigned long long)c.k_offset, c.sampler, part, acc, fin, g.nstages);
+        (unsigned long long)c.k_offset, c.sampler, part, acc, fin, g.nstages, finalize ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -566,13 +572,13 @@ cudaError_t configure_step(const LaunchCtx &c)
 
 cudaError_t launch_step(const LaunchCtx &c, const CUtensorMap &tmap, float *eps, float *U,
                         const ProblemDev *prob, float *S, CtlDev *ctl, float *part, long long *acc,
-                        float *U_prev, float *next_act, unsigned flags)
+                        float *U_prev, float *next_act, unsigned flags, bool finalize)
 {
     FinalizeArgs fin{U, U_prev, next_act, c.horizon, c.act_dim, flags};
 #define MPPI_STEP_CASE(A_)                                                                       \
     case A_:                                                                                     \
-        return c.strict ? launch_step_t<A_, true>(c, tmap, eps, U, prob, S, ctl, part, acc, fin) \
-                        : launch_step_t<A_, false>(c, tmap, eps, U, prob, S, ctl, part, acc, fin)
+        return c.strict ? launch_step_t<A_, true>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize) \
+                        : launch_step_t<A_, false>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize)
     switch (c.act_dim) {
         MPPI_STEP_CASE(1);
         MPPI_STEP_CASE(2);

@@ -70,7 +70,56 @@ def gloo_mode():
     dist.destroy_process_group()
 
 
-def gpu_mode(comm):
+def gloo_merge_mode():
+    """CPU mirror of xchg_merge_finalize_kernel (csrc/kernels.cu): shard-local softmax reference,
+    all-gather of {key, fixed-point accumulators}, rescale, sum in rank order."""
+    from mppi_gpu_b200 import capi
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    K, T, A, lam = 1501, 19, 3, 0.7
+    cfg = REF_CFG[A]
+    x0, U, eps = make_inputs(K, T, A, seed=78, sigma=0.3)
+    k0, k1 = capi.shard_range(K, rank, world)
+    p = po.make_problem(k1 - k0, T, A, 0.1, cfg["goal"], cfg["w"], lam=lam)
+    S = po.rollout_all(p, x0, U, eps[k0:k1])
+    keys = (ordered(S) << np.uint64(32)) | np.arange(k0, k1, dtype=np.uint64)
+    my_key = int(keys.min())
+    beta_r = S.min()
+    wt = po.exp(S, lam, beta_r)                       # relative to the shard's own minimum
+    num = (wt[:, None].astype(np.float64) * eps[k0:k1].reshape(k1 - k0, T * A)).sum(0)
+    acc = np.rint(np.concatenate([num.astype(np.float32), [wt.sum(dtype=np.float32)]])
+                  .astype(np.float64) * ACC_SCALE).astype(np.int64)
+    msg = torch.from_numpy(np.concatenate([[my_key - (1 << 63)], acc]).astype(np.int64))
+    box = [torch.zeros_like(msg) for _ in range(world)]
+    dist.all_gather(box, msg)
+    gkeys = [int(b[0].item()) + (1 << 63) for b in box]
+    gkey = min(gkeys)
+
+    def key_beta(k):
+        o = np.uint32(k >> 32)
+        return (np.uint32(o & 0x7FFFFFFF) if o & 0x80000000 else np.uint32(~o)).view(np.float32)
+
+    beta = key_beta(gkey)
+    nil = np.float32(-(np.float32(1) / np.float32(lam)))
+    tot = np.zeros(T * A + 1, np.float64)
+    for r in range(world):
+        f = np.exp(np.float32(nil * np.float32(key_beta(gkeys[r]) - beta)), dtype=np.float32)
+        tot += box[r][1:].numpy().astype(np.float64) * float(f)
+    tot = np.rint(tot) / ACC_SCALE
+    Un = U.ravel() + (tot[:-1] / tot[-1]).astype(np.float32)
+    Un = po.shift(Un, T, A)
+    pf = po.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], lam=lam)
+    ref = po.step(pf, x0, U, eps)
+    assert (gkey & 0xFFFFFFFF) == ref["argmin"] and beta == ref["beta"]
+    assert np.allclose(Un, ref["U"].ravel(), rtol=1e-5, atol=1e-6), np.abs(Un - ref["U"].ravel()).max()
+    assert abs(tot[-1] - float(ref["eta"])) <= 1e-5 * float(ref["eta"])
+    dist.barrier()
+    if rank == 0:
+        print("GLOO_MERGE_OK")
+    dist.destroy_process_group()
+
+
+def gpu_mode(comm, flags=0):
     from mppi_gpu_b200 import capi
     from mppi_gpu_b200.torch_dist import sharded_controller
     rank = int(os.environ["RANK"])
@@ -82,7 +131,8 @@ def gpu_mode(comm):
     K, T, A, lam = 20003, 40, 3, 5.0
     cfg = REF_CFG[A]
     x0, U, _ = make_inputs(K, T, A, seed=3)
-    ctl = sharded_controller(K, T, 0.1, 2 * A, A, comm=comm, device=local, lam=lam, seed=11)
+    ctl = sharded_controller(K, T, 0.1, 2 * A, A, comm=comm, device=local, lam=lam, seed=11,
+                             flags=flags)
     k0, k1 = capi.shard_range(K, rank, world)
     assert (ctl.k_offset, ctl.k_local) == (k0, k1 - k0)
     ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
@@ -136,8 +186,10 @@ if __name__ == "__main__":
     try:
         if sys.argv[1] == "gloo":
             gloo_mode()
+        elif sys.argv[1] == "gloo_merge":
+            gloo_merge_mode()
         else:
-            gpu_mode(sys.argv[1])
+            gpu_mode(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     except BaseException:
         traceback.print_exc()
         sys.stderr.flush()

@@ -10,10 +10,10 @@ from conftest import ROOT
 WORKER = os.path.join(ROOT, "tests", "dist_worker.py")
 
 
-def _launch(mode, nproc, port):
+def _launch(mode, nproc, port, *extra):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
-           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, mode]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, mode, *extra]
     return subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
 
 
@@ -25,6 +25,24 @@ def test_k_shard_exchange_logic_gloo_world2():
 def test_k_shard_exchange_logic_gloo_world3():
     r = _launch("gloo", 3, 29542)
     assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_k_shard_online_softmax_merge_gloo_world3():
+    """The single-exchange merge of the peer-mailbox path: every shard averages relative to its
+    own minimum, the shards' accumulators are rescaled by exp(-(beta_r-beta)/lambda) and summed."""
+    r = _launch("gloo_merge", 3, 29547)
+    assert r.returncode == 0 and "GLOO_MERGE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.gpu
+def test_k_sharded_one_kernel_step():
+    """K-shards running the one-kernel step, merged by the single peer-mailbox exchange."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    r = _launch("p2p", min(n, 4), 29548, "128")
+    assert r.returncode == 0 and "P2P_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 @pytest.mark.gpu
@@ -90,7 +108,8 @@ def test_single_process_device_group(oracle):
     ctl.get_act()
     kt = ctl.kernel_times()
     ctl.set_profiling(False)
-    assert kt["comm_min"][1] == 1 and kt["average"][1] == 1
+    # peer-mailbox shards merge with ONE exchange (online softmax): no beta exchange
+    assert kt["comm_min"][1] == 0 and kt["comm_sum"][1] == 1 and kt["average"][1] == 1
     single.close()
     ctl.close()
 
