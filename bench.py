@@ -215,6 +215,8 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     elif k_loc >= 400000:
         # (K-shards: the one-kernel step needs the single-exchange peer-mailbox merge)
         flags = capi.FLAG_STEP_KERNEL if (world == 1 or args.comm == "p2p") else capi.FLAG_FUSED_SAMPLING
+    elif k_loc >= 120000:
+        flags = capi.FLAG_FUSED_SAMPLING          # two kernels; measured faster down to ~1e5 samples
     else:
         flags = 0
     if world > 1:
