@@ -210,21 +210,14 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     # rollout wins.
     k_loc = capi.shard_range(K, rank, world)
     k_loc = k_loc[1] - k_loc[0]
-    if args.flags >= 0:
-        flags = args.flags
-    elif k_loc >= 400000:
-        # (K-shards: the one-kernel step needs the single-exchange peer-mailbox merge)
-        flags = capi.FLAG_STEP_KERNEL if (world == 1 or args.comm == "p2p") else capi.FLAG_FUSED_SAMPLING
-    elif k_loc >= 120000:
-        flags = capi.FLAG_FUSED_SAMPLING          # two kernels; measured faster down to ~1e5 samples
-    else:
-        flags = 0
+    flags = args.flags if args.flags >= 0 else capi.FLAG_AUTO_CHAIN
     if world > 1:
         from mppi_gpu_b200.torch_dist import sharded_controller
         ctl = sharded_controller(K, T, dt, 2 * A, A, comm=args.comm, device=local_rank, seed=0,
                                  flags=flags)
     else:
         ctl = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=flags, device=local_rank)
+    flags = ctl.flags()                       # MPPI_FLAG_AUTO_CHAIN resolved by the library
     x0 = np.zeros(2 * A, np.float32)
     ctl.memcpy_set_data(x0, np.zeros((T, A), np.float32), goal, w)
 
@@ -429,8 +422,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--flags", type=int, default=-1,
-                    help="MPPI_FLAG_* bits; default with >= 4e5 samples/GPU: the one-kernel step (128) "
-                         "on one GPU, fused sampling (32) on K-shards")
+                    help="MPPI_FLAG_* bits; default MPPI_FLAG_AUTO_CHAIN: >= 4e5 samples/GPU the one-kernel "
+                         "step (128), >= 1.2e5 fused sampling (32), else the unfused chain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="K-shard exchange for --gpus > 1: NVLink peer mailboxes or NCCL")

@@ -71,6 +71,13 @@ extern "C" {
                                                the shared-memory row sums; otherwise the step
                                                silently uses the kernel chain                */
 
+#define MPPI_FLAG_AUTO_CHAIN      (1u << 8)  /* let the library pick the kernel chain from the
+                                               shard size (thresholds measured on B200):
+                                               >= 4e5 samples: MPPI_FLAG_STEP_KERNEL (single
+                                               shard or MPPI_COMM_P2P), >= 1.2e5:
+                                               MPPI_FLAG_FUSED_SAMPLING, else the unfused
+                                               chain.  mppi_get_flags returns the choice.     */
+
 /* mppi_params.comm */
 #define MPPI_COMM_NONE  0   /* single shard                                          */
 #define MPPI_COMM_NCCL  1   /* ncclAllReduce(min) for beta, ncclAllReduce(sum) for the
@@ -178,6 +185,9 @@ int mppi_set_u(mppi_handle *h, const float *u);
  * weight [K_local].  K_local = this shard's samples (== K for one shard). */
 int mppi_get_info(mppi_handle *h, float *x, float *u, float *e, float *cost, float *beta,
                   float *nabla, float *weight);
+
+/* the flags the handle runs with (MPPI_FLAG_AUTO_CHAIN resolved to the chosen chain) */
+int mppi_get_flags(mppi_handle *h, uint32_t *flags);
 
 /* beta / eta / argmin / step counter of the last step */
 int mppi_get_step_info(mppi_handle *h, mppi_step_info *info);

@@ -39,7 +39,8 @@ public:
         const float *init_act = nullptr;   // [act_dim]; non-null enables init-act re-init
         const float *max_act = nullptr;    // [act_dim]; non-null enables clamping
         unsigned long long seed = 0;
-        unsigned flags = 0;                // extra MPPI_FLAG_* bits
+        unsigned flags = MPPI_FLAG_AUTO_CHAIN;   // MPPI_FLAG_* bits; default: the library picks
+                                                 // the fastest kernel chain for the shard size
         int device = 0;
         const int *devices = nullptr;      // non-null: shard K over these GPUs (one process)
         int num_devices = 0;

@@ -28,6 +28,7 @@ FLAG_NO_GRAPH = 1 << 4
 FLAG_FUSED_SAMPLING = 1 << 5
 FLAG_SPLIT_KERNELS = 1 << 6
 FLAG_STEP_KERNEL = 1 << 7
+FLAG_AUTO_CHAIN = 1 << 8
 
 COMM_NONE, COMM_NCCL, COMM_P2P = 0, 1, 2
 P2P_HANDLE_BYTES = 64
@@ -38,7 +39,7 @@ K_SAMPLE, K_ROLLOUT, K_COMM_MIN, K_WEIGHTS, K_AVERAGE, K_COMM_SUM, K_FINALIZE, K
 EXPORTS = [
     "mppi_params_default", "mppi_create", "mppi_create_multi", "mppi_destroy", "mppi_set_problem", "mppi_set_state",
     "mppi_step", "mppi_step_enqueue", "mppi_step_wait", "mppi_get_u", "mppi_set_u",
-    "mppi_get_info", "mppi_get_step_info", "mppi_set_noise", "mppi_set_noise_mode",
+    "mppi_get_info", "mppi_get_flags", "mppi_get_step_info", "mppi_set_noise", "mppi_set_noise_mode",
     "mppi_sample_only", "mppi_shard_range", "mppi_local_samples", "mppi_timer_start", "mppi_timer_stop",
     "mppi_set_profiling", "mppi_get_kernel_times", "mppi_get_launch_count", "mppi_kernel_name",
     "mppi_comm_unique_id", "mppi_comm_p2p_handle", "mppi_comm_p2p_connect", "mppi_last_error",
@@ -112,6 +113,7 @@ def load():
     L.mppi_get_u.argtypes = [H, fp]
     L.mppi_set_u.argtypes = [H, fp]
     L.mppi_get_info.argtypes = [H, fp, fp, fp, fp, fp, fp, fp]
+    L.mppi_get_flags.argtypes = [H, C.POINTER(C.c_uint32)]
     L.mppi_get_step_info.argtypes = [H, C.POINTER(MppiStepInfo)]
     L.mppi_set_noise.argtypes = [H, fp]
     L.mppi_set_noise_mode.argtypes = [H, C.c_int]

@@ -131,6 +131,12 @@ class PointMassModel:
         return dict(beta=np.float32(info.beta), eta=np.float32(info.eta),
                     argmin=int(info.argmin), step=int(info.step))
 
+    def flags(self):
+        """MPPI_FLAG_* bits the handle runs with (FLAG_AUTO_CHAIN resolved)."""
+        f = C.c_uint32()
+        capi.check(self._lib.mppi_get_flags(self._h, C.byref(f)))
+        return int(f.value)
+
     def timer_start(self):
         capi.check(self._lib.mppi_timer_start(self._h))
 

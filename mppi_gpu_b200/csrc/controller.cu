@@ -479,7 +479,18 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     CKH(cudaEventCreate(&h->t0));
     CKH(cudaEventCreate(&h->t1));
     CKH(configure_kernels(c));
-    if ((p.flags & MPPI_FLAG_STEP_KERNEL) && step_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms)) {
+    if (p.flags & MPPI_FLAG_AUTO_CHAIN) {
+        // thresholds measured on B200 at T=200 (tools/quick_prof.py): the one-kernel step wins once
+        // every rollout warp runs more than ~1.7 tiles, the fused two-kernel chain down to ~1e5
+        const bool can_step = (p.world_size == 1 || p.comm == MPPI_COMM_P2P) &&
+                              step_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms);
+        if (!(p.flags & MPPI_FLAG_SPLIT_KERNELS)) {
+            if (c.k_local >= 400000 && can_step) h->p.flags |= MPPI_FLAG_STEP_KERNEL;
+            else if (c.k_local >= 120000)        h->p.flags |= MPPI_FLAG_FUSED_SAMPLING;
+        }
+        h->p.flags &= ~MPPI_FLAG_AUTO_CHAIN;
+    }
+    if ((h->p.flags & MPPI_FLAG_STEP_KERNEL) && step_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms)) {
         CKH(configure_step(c));
         CKH(cudaMalloc(&h->d_part, sizeof(float) * step_part_floats(c)));
         CKH(cudaMemsetAsync(h->d_part, 0, sizeof(float) * step_part_floats(c), h->stream));
@@ -746,6 +757,14 @@ int mppi_get_u(mppi_handle *h, float *u)
     if (!u) return fail(MPPI_ERR_INVALID, "null argument");
     CK(cudaMemcpyAsync(u, h->d_U, sizeof(float) * h->R, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_get_flags(mppi_handle *h, uint32_t *flags)
+{
+    if (h && !h->children.empty()) return mppi_get_flags(h->children[0], flags);
+    if (!h || !flags) return fail(MPPI_ERR_INVALID, "null argument");
+    *flags = h->p.flags;
     return MPPI_OK;
 }
 

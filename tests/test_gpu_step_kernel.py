@@ -167,3 +167,25 @@ def test_step_kernel_full_size_point_mass3d(M, oracle):
     na = ctl.get_act()
     _assert_against_float64(oracle, ctl, na, U, x0, K, T, A, 1.0, cfg, stride=997)
     ctl.close()
+
+
+def test_auto_chain_picks_by_shard_size(M):
+    """MPPI_FLAG_AUTO_CHAIN: the library resolves the kernel chain from the shard size and
+    reports its choice; whatever it picks draws the same noise and produces the same costs."""
+    from mppi_gpu_b200 import capi
+    T, A = 10, 2
+    cfg = REF_CFG[A]
+    want = {50000: 0, 150000: capi.FLAG_FUSED_SAMPLING, 450000: capi.FLAG_STEP_KERNEL}
+    for K, chain in want.items():
+        ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=4, flags=capi.FLAG_AUTO_CHAIN)
+        assert ctl.flags() == chain, (K, ctl.flags())
+        ctl.memcpy_set_data(np.zeros(4), np.zeros((T, A)), cfg["goal"], cfg["w"])
+        na = ctl.get_act()
+        cost = ctl.get_inf(want_e=False)["cost"]
+        ctl.close()
+        ref = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=4, flags=0)
+        ref.memcpy_set_data(np.zeros(4), np.zeros((T, A)), cfg["goal"], cfg["w"])
+        na0 = ref.get_act()
+        assert np.array_equal(bits(ref.get_inf(want_e=False)["cost"]), bits(cost))
+        assert _close(na, na0, tol=2e-6)
+        ref.close()
