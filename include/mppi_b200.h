@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MPPI_ABI_VERSION 1
+#define MPPI_ABI_VERSION 2
 #define MPPI_MAX_ACT 4            /* supported action dims: 1..4 (state dim = 2A) */
 #define MPPI_COMM_ID_BYTES 128
 
@@ -87,6 +87,15 @@ extern "C" {
                                kernel on the step's critical path                    */
 #define MPPI_P2P_HANDLE_BYTES 64
 
+/* mppi_params.model: the dynamics functor the rollout kernels are instantiated on (the cost
+ * is Cost::step_cost / final_cost for both) */
+#define MPPI_MODEL_POINT_MASS   0   /* the reference's double integrator: gains {1,dt,0,1} /
+                                       {dt^2/2,dt} formed from dt as in src/point_mass.cu:46-51 */
+#define MPPI_MODEL_LINEAR_AXIS  1   /* per action dim  p' = g0 p + g1 v + b0 (u+e),
+                                       v' = g2 p + g3 v + b1 (u+e)  with caller-given gains
+                                       (the arguments of PointMassModelGpu::init,
+                                       src/point_mass_gpu.cu:25-39): damped / geared point masses */
+
 typedef struct mppi_handle mppi_handle;
 
 /* Replaces the constructor arguments of PointMassModel (include/point_mass.hpp:25-30:
@@ -113,6 +122,10 @@ typedef struct mppi_params {
     int32_t  world_size;                /* K is split into world_size contiguous shards */
     int32_t  comm;                      /* MPPI_COMM_*                                */
     uint8_t  comm_id[MPPI_COMM_ID_BYTES]; /* ncclUniqueId from mppi_comm_unique_id     */
+    int32_t  model;                     /* MPPI_MODEL_*                               */
+    float    state_gain[4];             /* {g0,g1,g2,g3}, MPPI_MODEL_LINEAR_AXIS only */
+    float    act_gain[2];               /* {b0,b1},       MPPI_MODEL_LINEAR_AXIS only */
+    int32_t  reserved_;
 } mppi_params;
 
 /* per-step scalars, the reference's _beta / _nabla (src/point_mass.cu:250-257) */

@@ -42,6 +42,9 @@ public:
         unsigned flags = MPPI_FLAG_AUTO_CHAIN;   // MPPI_FLAG_* bits; default: the library picks
                                                  // the fastest kernel chain for the shard size
         int device = 0;
+        const float *state_gain = nullptr; // [4] + act_gain [2]: MPPI_MODEL_LINEAR_AXIS (the gains
+        const float *act_gain = nullptr;   // PointMassModelGpu::init takes) instead of the
+                                           // double integrator formed from dt
         const int *devices = nullptr;      // non-null: shard K over these GPUs (one process)
         int num_devices = 0;
     };
@@ -70,6 +73,12 @@ public:
             if (o.inv_sigma) p.inv_sigma[a] = o.inv_sigma[a];
             if (o.init_act) p.init_act[a] = o.init_act[a];
             if (o.max_act) p.max_act[a] = o.max_act[a];
+        }
+        if (o.state_gain && o.act_gain) {
+            p.model = MPPI_MODEL_LINEAR_AXIS;
+            for (int i = 0; i < 4; ++i) p.state_gain[i] = o.state_gain[i];
+            p.act_gain[0] = o.act_gain[0];
+            p.act_gain[1] = o.act_gain[1];
         }
         if (o.init_act) p.flags |= MPPI_FLAG_REINIT_INIT_ACT;
         if (o.max_act) p.flags |= MPPI_FLAG_CLAMP_ACTIONS;

@@ -31,6 +31,7 @@ FLAG_STEP_KERNEL = 1 << 7
 FLAG_AUTO_CHAIN = 1 << 8
 
 COMM_NONE, COMM_NCCL, COMM_P2P = 0, 1, 2
+MODEL_POINT_MASS, MODEL_LINEAR_AXIS = 0, 1
 P2P_HANDLE_BYTES = 64
 
 K_SAMPLE, K_ROLLOUT, K_COMM_MIN, K_WEIGHTS, K_AVERAGE, K_COMM_SUM, K_FINALIZE, K_COUNT = range(8)
@@ -68,6 +69,10 @@ class MppiParams(C.Structure):
         ("world_size", C.c_int32),
         ("comm", C.c_int32),
         ("comm_id", C.c_uint8 * COMM_ID_BYTES),
+        ("model", C.c_int32),
+        ("state_gain", C.c_float * 4),
+        ("act_gain", C.c_float * 2),
+        ("reserved_", C.c_int32),
     ]
 
 
@@ -133,7 +138,7 @@ def load():
         fn = getattr(L, name)
         if name not in ("mppi_last_error", "mppi_kernel_name"):
             fn.restype = C.c_int
-    if L.mppi_abi_version() != 1:
+    if L.mppi_abi_version() != 2:
         raise ImportError("libmppi_b200.so ABI version mismatch")
     _lib = L
     return L

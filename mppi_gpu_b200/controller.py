@@ -20,7 +20,8 @@ class PointMassModel:
 
     def __init__(self, nb_sim, steps, dt, state_dim, act_dim, verbose=False, *, lam=1.0,
                  sigma=0.025, inv_sigma=1.0, init_act=0.0, max_act=1.0, seed=0, flags=0,
-                 device=0, rank=0, world_size=1, comm_id=None, comm=None, devices=None):
+                 device=0, rank=0, world_size=1, comm_id=None, comm=None, devices=None,
+                 state_gain=None, act_gain=None):
         self._lib = capi.load()
         p = capi.MppiParams()
         capi.check(self._lib.mppi_params_default(C.byref(p)))
@@ -34,6 +35,14 @@ class PointMassModel:
             for i, v in enumerate(arr):
                 getattr(p, name)[i] = float(v)
         p.seed, p.flags, p.device = int(seed), int(flags), int(device)
+        if state_gain is not None or act_gain is not None:
+            # MPPI_MODEL_LINEAR_AXIS: caller-given gains {g0,g1,g2,g3}, {b0,b1}
+            assert len(state_gain) == 4 and len(act_gain) == 2
+            p.model = capi.MODEL_LINEAR_AXIS
+            for i in range(4):
+                p.state_gain[i] = float(state_gain[i])
+            for i in range(2):
+                p.act_gain[i] = float(act_gain[i])
         p.rank, p.world_size = int(rank), int(world_size)
         if world_size > 1:
             p.comm = capi.COMM_NCCL if comm is None else int(comm)

@@ -269,6 +269,8 @@ int mppi_params_default(mppi_params *p)
     }
     p->world_size = 1;
     p->comm = MPPI_COMM_NONE;
+    p->model = MPPI_MODEL_POINT_MASS;
+    p->state_gain[0] = 1.0f; p->state_gain[3] = 1.0f;   /* identity until the caller fills them */
     return MPPI_OK;
 }
 
@@ -364,6 +366,8 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     if (p.horizon < 1 || (long long)p.horizon * p.act_dim > 32768)
         return fail(MPPI_ERR_INVALID, "horizon %d out of range", p.horizon);
     if (!(p.lambda > 0.0f)) return fail(MPPI_ERR_INVALID, "lambda must be > 0");
+    if (p.model != MPPI_MODEL_POINT_MASS && p.model != MPPI_MODEL_LINEAR_AXIS)
+        return fail(MPPI_ERR_INVALID, "model %d unknown", p.model);
     if (p.world_size < 1 || p.rank < 0 || p.rank >= p.world_size)
         return fail(MPPI_ERR_INVALID, "rank %d / world_size %d invalid", p.rank, p.world_size);
     if (p.world_size > 1 && p.comm != MPPI_COMM_NCCL && p.comm != MPPI_COMM_P2P)
@@ -406,6 +410,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     c.k_pad = (c.k_local + kKPad - 1) / kKPad * kKPad;
     c.seed = p.seed;
     c.strict = (p.flags & MPPI_FLAG_STRICT_ARITH) != 0;
+    c.general_gains = p.model == MPPI_MODEL_LINEAR_AXIS;
     c.num_sms = prop.multiProcessorCount;
     const long long ntiles = (c.k_pad / kAvgTileK) * (long long)((h->R + kAvgTileR - 1) / kAvgTileR);
     c.avg_grid = (int)(ntiles < c.num_sms ? ntiles : c.num_sms);
@@ -505,6 +510,11 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     pd.g[0] = 1.0f; pd.g[1] = dt; pd.g[2] = 0.0f; pd.g[3] = 1.0f;
     pd.b[0] = (float)((double)dt2 / 2.0);
     pd.b[1] = dt;
+    if (p.model == MPPI_MODEL_LINEAR_AXIS) {
+        for (int i = 0; i < 4; ++i) pd.g[i] = p.state_gain[i];
+        pd.b[0] = p.act_gain[0];
+        pd.b[1] = p.act_gain[1];
+    }
     pd.lambda = p.lambda;
     pd.neg_inv_lambda = -(1 / p.lambda);
     for (int a = 0; a < p.act_dim; ++a) {

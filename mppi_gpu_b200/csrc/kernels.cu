@@ -69,7 +69,7 @@ sample_kernel(float *__restrict__ eps, size_t ld, int T, int t_per_cta,
 // steps through a register double buffer: the loads of chunk c+1 are issued before the
 // arithmetic of chunk c, so every thread keeps CH*A vector loads (96 B for A=3) in flight.
 // SPT >= 2: the samples advance in pairs on the packed FP32x2 path (PointMass2).
-template <int A, bool STRICT, bool FUSED, int SPT>
+template <int A, class MODEL, bool FUSED, int SPT>
 __global__ void __launch_bounds__(256, (SPT == 1 ? 3 : 2))
 rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
                const float *__restrict__ U, const ProblemDev *__restrict__ prob,
@@ -103,8 +103,8 @@ rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
 
     if (SPT * g < ld) {
         // ---- per-thread state: scalar (SPT == 1) or packed pairs
-        PointMass<A, STRICT> m1;
-        PointMass2<A, STRICT> m2;
+        PointMass<A, MODEL> m1;
+        PointMass2<A, MODEL> m2;
         float x1[2 * A], c1 = 0.0f;
         f2 x2[NP][2 * A], c2[NP];
         if constexpr (PACKED) {
@@ -267,7 +267,7 @@ size_t rollout_tma_smem_bytes(int T, int W)
            (size_t)T * UStage<A>::kStride * sizeof(float) + 2 * kRtStages * sizeof(uint64_t) + 128;
 }
 
-template <int A, bool STRICT, int W>
+template <int A, class MODEL, int W>
 __global__ void __launch_bounds__(W + 32, (W == 256 ? 3 : W == 128 ? 6 : 8))
 rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long long k_local,
                    int T, const float *__restrict__ U, const ProblemDev *__restrict__ prob,
@@ -323,7 +323,7 @@ rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long
         }
         __syncwarp();
     } else {
-        PointMass<A, STRICT> m;
+        PointMass<A, MODEL> m;
         m.load(prob);
         int stage = 0;
         uint32_t phase = 0;
@@ -833,7 +833,7 @@ norm_weights_kernel(const float *__restrict__ S, long long k_local, float lambda
     w_out[k] = (float)(inv_eta * (double)expf(arg));
 }
 
-template <int A, bool STRICT>
+template <int A, class MODEL>
 __global__ void __launch_bounds__(128)
 trajectories_kernel(const float *__restrict__ eps, size_t ld, long long k_local, int T,
                     const float *__restrict__ U, const ProblemDev *__restrict__ prob,
@@ -841,7 +841,7 @@ trajectories_kernel(const float *__restrict__ eps, size_t ld, long long k_local,
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= k_local) return;
-    PointMass<A, STRICT> m;
+    PointMass<A, MODEL> m;
     m.load(prob);
     float x[2 * A], c = 0.0f;
 #pragma unroll
@@ -885,6 +885,25 @@ __global__ void clear_ctl_kernel(CtlDev *ctl)
         default: return cudaErrorInvalidValue;                          \
     }
 
+// every model a handle can select: {strict, fma} x {DoubleIntegrator, LinearAxis}
+#define MPPI_DISPATCH_MODEL(c_, ...)                                                     \
+    do {                                                                                 \
+        if ((c_).general_gains) {                                                        \
+            if ((c_).strict) { using kM = Model<true, LinearAxis>; __VA_ARGS__; }        \
+            else             { using kM = Model<false, LinearAxis>; __VA_ARGS__; }       \
+        } else {                                                                         \
+            if ((c_).strict) { using kM = Model<true, DoubleIntegrator>; __VA_ARGS__; }  \
+            else             { using kM = Model<false, DoubleIntegrator>; __VA_ARGS__; } \
+        }                                                                                \
+    } while (0)
+#define MPPI_FOR_EACH_MODEL(...)                                                         \
+    do {                                                                                 \
+        { using kM = Model<true, DoubleIntegrator>; __VA_ARGS__; }                       \
+        { using kM = Model<false, DoubleIntegrator>; __VA_ARGS__; }                      \
+        { using kM = Model<true, LinearAxis>; __VA_ARGS__; }                             \
+        { using kM = Model<false, LinearAxis>; __VA_ARGS__; }                            \
+    } while (0)
+
 cudaError_t launch_sample(const LaunchCtx &c, float *eps, const CtlDev *ctl,
                           bool use_step_override, unsigned long long step_override)
 {
@@ -901,7 +920,7 @@ cudaError_t launch_sample(const LaunchCtx &c, float *eps, const CtlDev *ctl,
     return cudaGetLastError();
 }
 
-template <int A, bool STRICT, bool FUSED, int SPT>
+template <int A, class MODEL, bool FUSED, int SPT>
 static cudaError_t launch_rollout_t(const LaunchCtx &c, float *eps, const float *U,
                                     const ProblemDev *prob, float *S, CtlDev *ctl)
 {
@@ -909,21 +928,21 @@ static cudaError_t launch_rollout_t(const LaunchCtx &c, float *eps, const float 
     const unsigned grid = (unsigned)((groups + 255) / 256);
     const size_t smem = sizeof(float) * (size_t)c.horizon *
                         (SPT >= 2 ? UStage2<A>::kStride : UStage<A>::kStride);
-    rollout_kernel<A, STRICT, FUSED, SPT><<<grid, 256, smem, c.stream>>>(
+    rollout_kernel<A, MODEL, FUSED, SPT><<<grid, 256, smem, c.stream>>>(
         eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U, prob, S, ctl,
         (unsigned long long)c.k_offset, c.sampler);
     return cudaGetLastError();
 }
 
-template <int A, bool STRICT>
+template <int A, class MODEL>
 static cudaError_t launch_rollout_a(const LaunchCtx &c, float *eps, const float *U,
                                     const ProblemDev *prob, float *S, CtlDev *ctl, bool fused)
 {
-    if (fused) return launch_rollout_t<A, STRICT, true, 4>(c, eps, U, prob, S, ctl);
+    if (fused) return launch_rollout_t<A, MODEL, true, 4>(c, eps, U, prob, S, ctl);
     switch (c.rollout_spt) {
-        case 1: return launch_rollout_t<A, STRICT, false, 1>(c, eps, U, prob, S, ctl);
-        case 2: return launch_rollout_t<A, STRICT, false, 2>(c, eps, U, prob, S, ctl);
-        default: return launch_rollout_t<A, STRICT, false, 4>(c, eps, U, prob, S, ctl);
+        case 1: return launch_rollout_t<A, MODEL, false, 1>(c, eps, U, prob, S, ctl);
+        case 2: return launch_rollout_t<A, MODEL, false, 2>(c, eps, U, prob, S, ctl);
+        default: return launch_rollout_t<A, MODEL, false, 4>(c, eps, U, prob, S, ctl);
     }
 }
 
@@ -931,32 +950,31 @@ cudaError_t launch_rollout(const LaunchCtx &c, float *eps, const float *U, const
                            float *S, CtlDev *ctl, bool fused)
 {
     MPPI_DISPATCH_A(c.act_dim,
-        return c.strict ? launch_rollout_a<kA, true>(c, eps, U, prob, S, ctl, fused)
-                        : launch_rollout_a<kA, false>(c, eps, U, prob, S, ctl, fused));
+        MPPI_DISPATCH_MODEL(c, return launch_rollout_a<kA, kM>(c, eps, U, prob, S, ctl, fused)));
     return cudaSuccess;
 }
 
-template <int A, bool STRICT, int W>
+template <int A, class MODEL, int W>
 static cudaError_t launch_rollout_tma_w(const LaunchCtx &c, const CUtensorMap &tmap, const float *U,
                                         const ProblemDev *prob, float *S, CtlDev *ctl)
 {
     const int nslab = (int)(c.k_pad / W);
     const int per_sm = (W == 256 ? 3 : W == 128 ? 6 : 8);
     const int grid = nslab < per_sm * c.num_sms ? nslab : per_sm * c.num_sms;
-    rollout_tma_kernel<A, STRICT, W><<<grid, W + 32, rollout_tma_smem_bytes<A>(c.horizon, W), c.stream>>>(
+    rollout_tma_kernel<A, MODEL, W><<<grid, W + 32, rollout_tma_smem_bytes<A>(c.horizon, W), c.stream>>>(
         tmap, nslab, (long long)c.k_local, c.horizon, U, prob, S, ctl,
         (unsigned long long)c.k_offset);
     return cudaGetLastError();
 }
 
-template <int A, bool STRICT>
+template <int A, class MODEL>
 static cudaError_t launch_rollout_tma_t(const LaunchCtx &c, const CUtensorMap &tmap, const float *U,
                                         const ProblemDev *prob, float *S, CtlDev *ctl)
 {
     switch (c.rollout_tma_width) {
-        case 64:  return launch_rollout_tma_w<A, STRICT, 64>(c, tmap, U, prob, S, ctl);
-        case 128: return launch_rollout_tma_w<A, STRICT, 128>(c, tmap, U, prob, S, ctl);
-        default:  return launch_rollout_tma_w<A, STRICT, 256>(c, tmap, U, prob, S, ctl);
+        case 64:  return launch_rollout_tma_w<A, MODEL, 64>(c, tmap, U, prob, S, ctl);
+        case 128: return launch_rollout_tma_w<A, MODEL, 128>(c, tmap, U, prob, S, ctl);
+        default:  return launch_rollout_tma_w<A, MODEL, 256>(c, tmap, U, prob, S, ctl);
     }
 }
 
@@ -964,15 +982,14 @@ cudaError_t launch_rollout_tma(const LaunchCtx &c, const CUtensorMap &tmap, cons
                                const ProblemDev *prob, float *S, CtlDev *ctl)
 {
     MPPI_DISPATCH_A(c.act_dim,
-        return c.strict ? launch_rollout_tma_t<kA, true>(c, tmap, U, prob, S, ctl)
-                        : launch_rollout_tma_t<kA, false>(c, tmap, U, prob, S, ctl));
+        MPPI_DISPATCH_MODEL(c, return launch_rollout_tma_t<kA, kM>(c, tmap, U, prob, S, ctl)));
     return cudaSuccess;
 }
 
-template <int A, bool STRICT, int W>
+template <int A, class MODEL, int W>
 static cudaError_t configure_rollout_tma_w(int T)
 {
-    return cudaFuncSetAttribute(rollout_tma_kernel<A, STRICT, W>,
+    return cudaFuncSetAttribute(rollout_tma_kernel<A, MODEL, W>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)rollout_tma_smem_bytes<A>(T, W));
 }
@@ -980,12 +997,11 @@ template <int A>
 static cudaError_t configure_rollout_tma(int T)
 {
     cudaError_t e;
-    if ((e = configure_rollout_tma_w<A, true, 64>(T)) != cudaSuccess) return e;
-    if ((e = configure_rollout_tma_w<A, true, 128>(T)) != cudaSuccess) return e;
-    if ((e = configure_rollout_tma_w<A, true, 256>(T)) != cudaSuccess) return e;
-    if ((e = configure_rollout_tma_w<A, false, 64>(T)) != cudaSuccess) return e;
-    if ((e = configure_rollout_tma_w<A, false, 128>(T)) != cudaSuccess) return e;
-    return configure_rollout_tma_w<A, false, 256>(T);
+    MPPI_FOR_EACH_MODEL(
+        if ((e = configure_rollout_tma_w<A, kM, 64>(T)) != cudaSuccess) return e;
+        if ((e = configure_rollout_tma_w<A, kM, 128>(T)) != cudaSuccess) return e;
+        if ((e = configure_rollout_tma_w<A, kM, 256>(T)) != cudaSuccess) return e);
+    return cudaSuccess;
 }
 
 int rollout_tma_rows(int A)
@@ -1103,37 +1119,34 @@ cudaError_t launch_trajectories(const LaunchCtx &c, const float *eps, const floa
 {
     const unsigned grid = (unsigned)((c.k_local + 127) / 128);
     MPPI_DISPATCH_A(c.act_dim,
-        if (c.strict)
-            trajectories_kernel<kA, true><<<grid, 128, 0, c.stream>>>(
-                eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U_prev, prob, x_out);
-        else
-            trajectories_kernel<kA, false><<<grid, 128, 0, c.stream>>>(
-                eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U_prev, prob, x_out));
+        MPPI_DISPATCH_MODEL(c, (trajectories_kernel<kA, kM><<<grid, 128, 0, c.stream>>>(
+            eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U_prev, prob, x_out))));
     return cudaGetLastError();
 }
 
 // Per-device one-time opt-in to large dynamic shared memory (called from mppi_create).
-template <int A, bool STRICT>
+template <int A, class MODEL>
 static cudaError_t configure_rollout_s(int smem)
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(rollout_kernel<A, STRICT, true, 4>,
+    e = cudaFuncSetAttribute(rollout_kernel<A, MODEL, true, 4>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rollout_kernel<A, STRICT, false, 4>,
+    e = cudaFuncSetAttribute(rollout_kernel<A, MODEL, false, 4>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rollout_kernel<A, STRICT, false, 2>,
+    e = cudaFuncSetAttribute(rollout_kernel<A, MODEL, false, 2>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(rollout_kernel<A, STRICT, false, 1>,
+    return cudaFuncSetAttribute(rollout_kernel<A, MODEL, false, 1>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 template <int A>
 static cudaError_t configure_rollout(int smem)
 {
-    cudaError_t e = configure_rollout_s<A, true>(smem);
-    return e != cudaSuccess ? e : configure_rollout_s<A, false>(smem);
+    cudaError_t e = cudaSuccess;
+    MPPI_FOR_EACH_MODEL(if ((e = configure_rollout_s<A, kM>(smem)) != cudaSuccess) return e);
+    return e;
 }
 
 cudaError_t configure_kernels(const LaunchCtx &c)

@@ -27,6 +27,7 @@ struct LaunchCtx {
     int64_t k_offset;      // global index of local sample 0 (multiple of 4)
     unsigned long long seed;
     bool strict;           // MPPI_FLAG_STRICT_ARITH
+    bool general_gains;    // MPPI_MODEL_LINEAR_AXIS: LinearAxis dynamics instead of DoubleIntegrator
     int  num_sms;
     int  avg_grid;         // CTAs of the averaging kernel
     int  weights_blocks;   // CTAs of the weights kernel

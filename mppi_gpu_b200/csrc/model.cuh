@@ -1,61 +1,34 @@
-// model.cuh -- the point-mass dynamics and cost of the rollout (reference
-// PointMassModelGpu::step / Cost::step_cost / final_cost, src/point_mass_gpu.cu:82-121,
-// src/cost.cu:42-64) as device structs shared by every rollout kernel: scalar (PointMass),
-// packed FP32x2 on a pair of samples (PointMass2), and the shared-memory staging of U.
+// model.cuh -- the plug-in point of the rollout: dynamics and cost as device functors.
+//
+// A rollout kernel is instantiated per MODEL = Model<STRICT, Dynamics> (no virtual calls, no
+// per-sample objects: the reference keeps a 168-byte PointMassModelGpu and a 48-byte Cost per
+// sample, include/point_mass_gpu.hpp:46-90, include/cost.hpp:32-46).  A functor has a scalar
+// form (one sample) and a packed FP32x2 form (a pair of samples, two lanes of one
+// instruction) with the same operations in the same order, so both give the same bits.
+//
+//   Dynamics::axis(p, v, ue) -> (p', v')      one action dimension of
+//       PointMassModelGpu::step (src/point_mass_gpu.cu:97-106):
+//       p' = g0*p + g1*v + b0*(u+e),  v' = g2*p + g3*v + b1*(u+e)
+//     DoubleIntegrator  the gains the reference's constructor hard-codes, {1,dt,0,1} /
+//                       {dt^2/2, dt} (src/point_mass.cu:46-51): g0*p == p and g2*p+g3*v == v
+//                       exactly, which saves three operations per axis and step;
+//     LinearAxis        any gains (PointMassModelGpu::init takes them as arguments,
+//                       src/point_mass_gpu.cu:25-39): damped / geared point masses such as
+//                       the MJCF plant of envs/point_mass2d.xml, README "generalize the code".
+//   QuadraticCost       Cost::step_cost / final_cost (src/cost.cu:42-64).
+//
+// Arithmetic.  STRICT rounds every product and sum separately in source order (== the
+// reference's host build, oracle ORACLE_ARITH_STRICT); otherwise the fused operations are
+// exactly those nvcc -fmad=true forms for the reference's device build (ORACLE_ARITH_FMA):
+// fma(b0,ue, fma(g0,p, g1*v)), fma((x-g)*w, (x-g), res), fma(u*inv_s, e, res).
+//
+// To add a model: write a Dynamics (or Cost) functor with load/axis/axis2, add a Model tag
+// to MPPI_DISPATCH_MODEL (kernels.cu / step.cu) and restate it in oracle/mppi_oracle.c.
 #pragma once
 
 #include "common.cuh"
 
 namespace mppi {
-
-template <int A, bool STRICT>
-struct PointMass {
-    float dt, b0, b1, lambda;
-    float goal[2 * A], w[2 * A];
-
-    __device__ __forceinline__ void load(const ProblemDev *__restrict__ p)
-    {
-        dt = p->g[1]; b0 = p->b[0]; b1 = p->b[1]; lambda = p->lambda;
-#pragma unroll
-        for (int i = 0; i < 2 * A; ++i) { goal[i] = p->goal[i]; w[i] = p->w[i]; }
-    }
-
-    // state cost  sum_i (x_i-g_i)*w_i*(x_i-g_i)  added onto res in index order
-    __device__ __forceinline__ float state_cost(const float (&x)[2 * A], float res) const
-    {
-#pragma unroll
-        for (int i = 0; i < 2 * A; ++i) {
-            const float d = __fsub_rn(x[i], goal[i]);
-            if (STRICT) res = __fadd_rn(res, __fmul_rn(__fmul_rn(d, w[i]), d));
-            else        res = __fmaf_rn(__fmul_rn(d, w[i]), d, res);
-        }
-        return res;
-    }
-
-    // one step: x <- f(x, u+e);  c += step_cost(x_new, u, e)
-    __device__ __forceinline__ void step(float (&x)[2 * A], float &c, const float (&u)[A],
-                                         const float (&ui)[A], const float (&e)[A]) const
-    {
-        float res = 0.0f;
-#pragma unroll
-        for (int i = 0; i < A; ++i) {
-            const float ue = __fadd_rn(u[i], e[i]);
-            const float p = x[i], v = x[i + A];
-            if (STRICT) {
-                x[i]     = __fadd_rn(__fadd_rn(p, __fmul_rn(dt, v)), __fmul_rn(b0, ue));
-                x[i + A] = __fadd_rn(v, __fmul_rn(b1, ue));
-                res = __fadd_rn(res, __fmul_rn(ui[i], e[i]));
-            } else {
-                x[i]     = __fmaf_rn(b0, ue, __fadd_rn(p, __fmul_rn(dt, v)));
-                x[i + A] = __fmaf_rn(b1, ue, v);
-                res = __fmaf_rn(ui[i], e[i], res);
-            }
-        }
-        res = __fmul_rn(res, lambda);
-        res = state_cost(x, res);
-        c = __fadd_rn(c, res);
-    }
-};
 
 // ---------------------------------------------------------------------------------
 // Packed FP32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2).  One instruction performs the
@@ -101,31 +74,210 @@ __device__ __forceinline__ f2 mulp2(f2 a, f2 b)
     return fma2(a, b, z);
 }
 
-// PointMass on a PAIR of samples: same operations, same order, two lanes.
-template <int A, bool STRICT>
-struct PointMass2 {
-    f2 dt, b0, b1, lambda;
-    f2 goal[2 * A], w[2 * A];
+// ---------------------------------------------------------------------------------
+// dynamics functors
+// ---------------------------------------------------------------------------------
+struct DoubleIntegrator {
+    float dt, b0, b1;
+    f2 dt2, b02, b12;
 
     __device__ __forceinline__ void load(const ProblemDev *__restrict__ p)
     {
-        dt = mk2(p->g[1], p->g[1]); b0 = mk2(p->b[0], p->b[0]); b1 = mk2(p->b[1], p->b[1]);
-        lambda = mk2(p->lambda, p->lambda);
-#pragma unroll
-        for (int i = 0; i < 2 * A; ++i) {
-            goal[i] = mk2(p->goal[i], p->goal[i]);
-            w[i] = mk2(p->w[i], p->w[i]);
+        dt = p->g[1]; b0 = p->b[0]; b1 = p->b[1];
+    }
+    __device__ __forceinline__ void load2(const ProblemDev *__restrict__ p)
+    {
+        dt2 = mk2(p->g[1], p->g[1]); b02 = mk2(p->b[0], p->b[0]); b12 = mk2(p->b[1], p->b[1]);
+    }
+    template <bool STRICT>
+    __device__ __forceinline__ void axis(float &p, float &v, float ue) const
+    {
+        if (STRICT) {
+            p = __fadd_rn(__fadd_rn(p, __fmul_rn(dt, v)), __fmul_rn(b0, ue));
+            v = __fadd_rn(v, __fmul_rn(b1, ue));
+        } else {
+            p = __fmaf_rn(b0, ue, __fadd_rn(p, __fmul_rn(dt, v)));
+            v = __fmaf_rn(b1, ue, v);
         }
     }
-    __device__ __forceinline__ f2 state_cost(const f2 (&x)[2 * A], f2 res) const
+    template <bool STRICT>
+    __device__ __forceinline__ void axis2(f2 &p, f2 &v, f2 ue) const
+    {
+        if (STRICT) {
+            p = add2(add2(p, mulp2(dt2, v)), mulp2(b02, ue));
+            v = add2(v, mulp2(b12, ue));
+        } else {
+            p = fma2(b02, ue, add2(p, mulp2(dt2, v)));
+            v = fma2(b12, ue, v);
+        }
+    }
+};
+
+struct LinearAxis {
+    float g0, g1, g2, g3, b0, b1;
+    f2 g02, g12, g22, g32, b02, b12;
+
+    __device__ __forceinline__ void load(const ProblemDev *__restrict__ p)
+    {
+        g0 = p->g[0]; g1 = p->g[1]; g2 = p->g[2]; g3 = p->g[3]; b0 = p->b[0]; b1 = p->b[1];
+    }
+    __device__ __forceinline__ void load2(const ProblemDev *__restrict__ p)
+    {
+        g02 = mk2(p->g[0], p->g[0]); g12 = mk2(p->g[1], p->g[1]);
+        g22 = mk2(p->g[2], p->g[2]); g32 = mk2(p->g[3], p->g[3]);
+        b02 = mk2(p->b[0], p->b[0]); b12 = mk2(p->b[1], p->b[1]);
+    }
+    template <bool STRICT>
+    __device__ __forceinline__ void axis(float &p, float &v, float ue) const
+    {
+        const float po = p, vo = v;          // both rows read the OLD state
+        if (STRICT) {
+            p = __fadd_rn(__fadd_rn(__fmul_rn(g0, po), __fmul_rn(g1, vo)), __fmul_rn(b0, ue));
+            v = __fadd_rn(__fadd_rn(__fmul_rn(g2, po), __fmul_rn(g3, vo)), __fmul_rn(b1, ue));
+        } else {
+            p = __fmaf_rn(b0, ue, __fmaf_rn(g0, po, __fmul_rn(g1, vo)));
+            v = __fmaf_rn(b1, ue, __fmaf_rn(g2, po, __fmul_rn(g3, vo)));
+        }
+    }
+    template <bool STRICT>
+    __device__ __forceinline__ void axis2(f2 &p, f2 &v, f2 ue) const
+    {
+        const f2 po = p, vo = v;
+        if (STRICT) {
+            p = add2(add2(mulp2(g02, po), mulp2(g12, vo)), mulp2(b02, ue));
+            v = add2(add2(mulp2(g22, po), mulp2(g32, vo)), mulp2(b12, ue));
+        } else {
+            p = fma2(b02, ue, fma2(g02, po, mulp2(g12, vo)));
+            v = fma2(b12, ue, fma2(g22, po, mulp2(g32, vo)));
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// cost functor: lambda * sum_a u_a*inv_s_a*e_a  +  sum_i (x_i-g_i)*w_i*(x_i-g_i)
+// ---------------------------------------------------------------------------------
+template <int A>
+struct QuadraticCost {
+    float lambda, goal[2 * A], w[2 * A];
+    f2 lambda2, goal2[2 * A], w2[2 * A];
+
+    __device__ __forceinline__ void load(const ProblemDev *__restrict__ p)
+    {
+        lambda = p->lambda;
+#pragma unroll
+        for (int i = 0; i < 2 * A; ++i) { goal[i] = p->goal[i]; w[i] = p->w[i]; }
+    }
+    __device__ __forceinline__ void load2(const ProblemDev *__restrict__ p)
+    {
+        lambda2 = mk2(p->lambda, p->lambda);
+#pragma unroll
+        for (int i = 0; i < 2 * A; ++i) {
+            goal2[i] = mk2(p->goal[i], p->goal[i]);
+            w2[i] = mk2(p->w[i], p->w[i]);
+        }
+    }
+    // state cost added onto res in index order (Cost::final_cost; second half of step_cost)
+    template <bool STRICT>
+    __device__ __forceinline__ float state(const float (&x)[2 * A], float res) const
     {
 #pragma unroll
         for (int i = 0; i < 2 * A; ++i) {
-            const f2 d = sub2(x[i], goal[i]);
-            if (STRICT) res = add2(res, mulp2(mul2(d, w[i]), d));
-            else        res = fma2(mul2(d, w[i]), d, res);
+            const float d = __fsub_rn(x[i], goal[i]);
+            if (STRICT) res = __fadd_rn(res, __fmul_rn(__fmul_rn(d, w[i]), d));
+            else        res = __fmaf_rn(__fmul_rn(d, w[i]), d, res);
         }
         return res;
+    }
+    template <bool STRICT>
+    __device__ __forceinline__ f2 state2(const f2 (&x)[2 * A], f2 res) const
+    {
+#pragma unroll
+        for (int i = 0; i < 2 * A; ++i) {
+            const f2 d = sub2(x[i], goal2[i]);
+            if (STRICT) res = add2(res, mulp2(mul2(d, w2[i]), d));
+            else        res = fma2(mul2(d, w2[i]), d, res);
+        }
+        return res;
+    }
+    // one term of the control cost, accumulated in action order
+    template <bool STRICT>
+    __device__ __forceinline__ float control(float res, float ui, float e) const
+    {
+        return STRICT ? __fadd_rn(res, __fmul_rn(ui, e)) : __fmaf_rn(ui, e, res);
+    }
+    template <bool STRICT>
+    __device__ __forceinline__ f2 control2(f2 res, f2 ui, f2 e) const
+    {
+        return STRICT ? add2(res, mulp2(ui, e)) : fma2(ui, e, res);
+    }
+    // stage cost from the finished control sum and the NEW state (Cost::step_cost)
+    template <bool STRICT>
+    __device__ __forceinline__ float stage(float ctrl, const float (&x)[2 * A]) const
+    {
+        return state<STRICT>(x, __fmul_rn(ctrl, lambda));
+    }
+    template <bool STRICT>
+    __device__ __forceinline__ f2 stage2(f2 ctrl, const f2 (&x)[2 * A]) const
+    {
+        // the product feeds an add when STRICT (see mulp2)
+        return state2<STRICT>(x, STRICT ? mulp2(ctrl, lambda2) : mul2(ctrl, lambda2));
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// model tag: what a rollout kernel is instantiated on
+// ---------------------------------------------------------------------------------
+template <bool STRICT_, class DYN_>
+struct Model {
+    static constexpr bool kStrict = STRICT_;
+    using Dyn = DYN_;
+};
+
+// one sample: x <- f(x, u+e);  c += step_cost(x_new, u, e)
+template <int A, class MODEL>
+struct PointMass {
+    static constexpr bool STRICT = MODEL::kStrict;
+    typename MODEL::Dyn dyn;
+    QuadraticCost<A> cost;
+
+    __device__ __forceinline__ void load(const ProblemDev *__restrict__ p)
+    {
+        dyn.load(p);
+        cost.load(p);
+    }
+    __device__ __forceinline__ float state_cost(const float (&x)[2 * A], float res) const
+    {
+        return cost.template state<STRICT>(x, res);
+    }
+    __device__ __forceinline__ void step(float (&x)[2 * A], float &c, const float (&u)[A],
+                                         const float (&ui)[A], const float (&e)[A]) const
+    {
+        float res = 0.0f;
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            const float ue = __fadd_rn(u[i], e[i]);
+            dyn.template axis<STRICT>(x[i], x[i + A], ue);
+            res = cost.template control<STRICT>(res, ui[i], e[i]);
+        }
+        c = __fadd_rn(c, cost.template stage<STRICT>(res, x));
+    }
+};
+
+// a PAIR of samples: same operations, same order, two lanes
+template <int A, class MODEL>
+struct PointMass2 {
+    static constexpr bool STRICT = MODEL::kStrict;
+    typename MODEL::Dyn dyn;
+    QuadraticCost<A> cost;
+
+    __device__ __forceinline__ void load(const ProblemDev *__restrict__ p)
+    {
+        dyn.load2(p);
+        cost.load2(p);
+    }
+    __device__ __forceinline__ f2 state_cost(const f2 (&x)[2 * A], f2 res) const
+    {
+        return cost.template state2<STRICT>(x, res);
     }
     __device__ __forceinline__ void step(f2 (&x)[2 * A], f2 &c, const f2 (&u)[A], const f2 (&ui)[A],
                                          const f2 (&e)[A]) const
@@ -134,20 +286,10 @@ struct PointMass2 {
 #pragma unroll
         for (int i = 0; i < A; ++i) {
             const f2 ue = add2(u[i], e[i]);
-            const f2 p = x[i], v = x[i + A];
-            if (STRICT) {
-                x[i]     = add2(add2(p, mulp2(dt, v)), mulp2(b0, ue));
-                x[i + A] = add2(v, mulp2(b1, ue));
-                res = add2(res, mulp2(ui[i], e[i]));
-            } else {
-                x[i]     = fma2(b0, ue, add2(p, mulp2(dt, v)));
-                x[i + A] = fma2(b1, ue, v);
-                res = fma2(ui[i], e[i], res);
-            }
+            dyn.template axis2<STRICT>(x[i], x[i + A], ue);
+            res = cost.template control2<STRICT>(res, ui[i], e[i]);
         }
-        res = STRICT ? mulp2(res, lambda) : mul2(res, lambda);   // feeds an add when STRICT
-        res = state_cost(x, res);
-        c = add2(c, res);
+        c = add2(c, cost.template stage2<STRICT>(res, x));
     }
 };
 

@@ -129,7 +129,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int count)
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
 }
 
-template <int A, bool STRICT, int NR>
+template <int A, class MODEL, int NR>
 __global__ void __launch_bounds__((NR + kStConsumers + 1) * 32, 1)
 step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ eps, size_t ld,
             long long k_local, int T, const float *U,
@@ -190,7 +190,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
 
     if (warp < NR) {
         // ================================ rollout ====================================
-        PointMass2<A, STRICT> m2;
+        PointMass2<A, MODEL> m2;
         m2.load(prob);
         const unsigned long long step = ctl->step;
         unsigned long long key = kMinKeyInit;
@@ -523,27 +523,34 @@ StepGeom step_geom(int T, int A, long long k_pad, int num_sms)
     return g;
 }
 
-template <int A, bool STRICT>
+template <int A, class MODEL>
 cudaError_t launch_step_t(const LaunchCtx &c, const CUtensorMap &tmap, float *eps, float *U,
                           const ProblemDev *prob, float *S, CtlDev *ctl, float *part,
                           long long *acc, const FinalizeArgs &fin, bool finalize)
 {
     const StepGeom g = step_geom(c.horizon, c.act_dim, c.k_pad, c.num_sms);
     if (g.nstages == 0) return cudaErrorInvalidConfiguration;
-    step_kernel<A, STRICT, kStepNR><<<g.grid, (kStepNR + kStConsumers + 1) * 32, g.smem, c.stream>>>(
+    step_kernel<A, MODEL, kStepNR><<<g.grid, (kStepNR + kStConsumers + 1) * 32, g.smem, c.stream>>>(
         tmap, eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U, prob, S, ctl,
         (unsigned long long)c.k_offset, c.sampler, part, acc, fin, g.nstages, finalize ? 1 : 0);
     return cudaGetLastError();
 }
 
+template <int A, class MODEL>
+cudaError_t configure_step_m(int smem)
+{
+    return cudaFuncSetAttribute(step_kernel<A, MODEL, kStepNR>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 template <int A>
 cudaError_t configure_step_a(int smem)
 {
-    cudaError_t e = cudaFuncSetAttribute(step_kernel<A, false, kStepNR>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(step_kernel<A, true, kStepNR>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e;
+    if ((e = configure_step_m<A, Model<false, DoubleIntegrator>>(smem)) != cudaSuccess) return e;
+    if ((e = configure_step_m<A, Model<true, DoubleIntegrator>>(smem)) != cudaSuccess) return e;
+    if ((e = configure_step_m<A, Model<false, LinearAxis>>(smem)) != cudaSuccess) return e;
+    return configure_step_m<A, Model<true, LinearAxis>>(smem);
 }
 }  // namespace
 
@@ -577,8 +584,11 @@ cudaError_t launch_step(const LaunchCtx &c, const CUtensorMap &tmap, float *eps,
     FinalizeArgs fin{U, U_prev, next_act, c.horizon, c.act_dim, flags};
 #define MPPI_STEP_CASE(A_)                                                                       \
     case A_:                                                                                     \
-        return c.strict ? launch_step_t<A_, true>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize) \
-                        : launch_step_t<A_, false>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize)
+        if (c.general_gains)                                                                     \
+            return c.strict ? launch_step_t<A_, Model<true, LinearAxis>>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize) \
+                            : launch_step_t<A_, Model<false, LinearAxis>>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize); \
+        return c.strict ? launch_step_t<A_, Model<true, DoubleIntegrator>>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize) \
+                        : launch_step_t<A_, Model<false, DoubleIntegrator>>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize)
     switch (c.act_dim) {
         MPPI_STEP_CASE(1);
         MPPI_STEP_CASE(2);

@@ -97,7 +97,12 @@ float oracle_rollout(const oracle_problem *p, const float *x0, const float *U,
     float *x = xa, *xn = xb;
     float c = 0.0f;                                   /* run(): _c = 0 */
 
-    oracle_gains(p->dt, g, b);
+    if (p->use_gains) {
+        for (int i = 0; i < 4; i++) g[i] = p->g[i];
+        b[0] = p->b[0]; b[1] = p->b[1];
+    } else {
+        oracle_gains(p->dt, g, b);
+    }
     for (int i = 0; i < S; i++) x[i] = x0[i];
     if (xtraj) memcpy(xtraj, x, sizeof(float) * S);
 

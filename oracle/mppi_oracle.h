@@ -42,6 +42,11 @@ typedef struct oracle_problem {
     float   inv_s[ORACLE_MAX_ACT];   /* reference hard-codes 1       */
     float   goal[2 * ORACLE_MAX_ACT];
     float   w[2 * ORACLE_MAX_ACT];
+    int32_t use_gains;               /* 0: gains from dt (reference constructor);
+                                        1: g / b below (the arguments of
+                                        PointMassModelGpu::init, src/point_mass_gpu.cu:25-39) */
+    float   g[4];
+    float   b[2];
 } oracle_problem;
 
 /* gains of the double integrator: src/point_mass.cu:46-51 */

@@ -25,11 +25,22 @@ class OracleProblem(C.Structure):
         ("inv_s", C.c_float * MAX_ACT),
         ("goal", C.c_float * (2 * MAX_ACT)),
         ("w", C.c_float * (2 * MAX_ACT)),
+        ("use_gains", C.c_int32),
+        ("g", C.c_float * 4),
+        ("b", C.c_float * 2),
     ]
 
 
-def make_problem(K, T, A, dt, goal, w, lam=1.0, inv_s=None, arith=ARITH_STRICT):
+def make_problem(K, T, A, dt, goal, w, lam=1.0, inv_s=None, arith=ARITH_STRICT, gains=None):
+    """gains = (state_gain[4], act_gain[2]) selects caller-given gains (the arguments of the
+    reference's PointMassModelGpu::init) instead of the double integrator formed from dt."""
     p = OracleProblem()
+    if gains is not None:
+        p.use_gains = 1
+        for i in range(4):
+            p.g[i] = float(gains[0][i])
+        for i in range(2):
+            p.b[i] = float(gains[1][i])
     p.K, p.T, p.A, p.arith = int(K), int(T), int(A), int(arith)
     p.dt, p.lambda_ = float(dt), float(lam)
     inv_s = [1.0] * A if inv_s is None else list(inv_s)
@@ -98,6 +109,10 @@ def ref():
         L.ref_rollout_costs.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _f32p,
                                         _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_int]
         L.ref_rollout_costs.restype = C.c_int
+        L.ref_rollout_costs_gains.argtypes = [C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_float,
+                                              _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p,
+                                              C.c_int]
+        L.ref_rollout_costs_gains.restype = C.c_int
         _ref = L
     return _ref
 
@@ -122,10 +137,18 @@ def rollout_all(p, x0, U, eps, want_traj=False, nthreads=1):
     return (S, xt) if want_traj else S
 
 
-def ref_rollout_all(K, T, A, dt, lam, x0, U, goal, w, eps, want_traj=False, nthreads=1):
+def ref_rollout_all(K, T, A, dt, lam, x0, U, goal, w, eps, want_traj=False, nthreads=1,
+                    gains=None):
     S = np.zeros(K, np.float32)
     xt = np.zeros((K, T + 1, 2 * A), np.float32) if want_traj else None
     e = _f32(eps).copy()
+    if gains is not None:
+        rc = ref().ref_rollout_costs_gains(K, T, A, _f32(gains[0]), _f32(gains[1]), float(lam),
+                                           _f32(x0), _f32(U), _f32(goal), _f32(w), e, S,
+                                           xt.ctypes.data if xt is not None else None,
+                                           int(nthreads))
+        assert rc == 0
+        return (S, xt) if want_traj else S
     rc = ref().ref_rollout_costs(K, T, A, float(dt), float(lam), _f32(x0), _f32(U), _f32(goal),
                                  _f32(w), e, S, xt.ctypes.data if xt is not None else None,
                                  int(nthreads))

@@ -88,11 +88,15 @@ extern "C" {
 /* K rollouts of the reference model.  eps is the reference layout [K,T,A] and is
  * left unchanged (run() copies it back onto itself through save_e()).
  * S_out [K]; xtraj [K,(T+1),2A] or NULL.  Returns 0. */
+static int ref_rollout_costs_impl(int K, int T, int A, float *state, float *act, float lambda,
+                                  const float *x0_in, const float *U_in, const float *goal_in,
+                                  const float *w_in, float *eps, float *S_out, float *xtraj,
+                                  int nthreads);
+
 int ref_rollout_costs(int K, int T, int A, float dt, float lambda, const float *x0_in,
                       const float *U_in, const float *goal_in, const float *w_in,
                       float *eps, float *S_out, float *xtraj, int nthreads)
 {
-    const int S = 2 * A;
     /* gains exactly as the reference constructor forms them, src/point_mass.cu:46-51 */
     float state[4];
     float act[2];
@@ -103,6 +107,29 @@ int ref_rollout_costs(int K, int T, int A, float dt, float lambda, const float *
     state[1] = _dt;
     state[2] = 0;
     state[3] = 1;
+    return ref_rollout_costs_impl(K, T, A, state, act, lambda, x0_in, U_in, goal_in, w_in, eps,
+                                  S_out, xtraj, nthreads);
+}
+
+/* the same with caller-given gains: PointMassModelGpu::init takes state_gain / act_gain as
+ * arguments (src/point_mass_gpu.cu:25-39); only the reference's constructor hard-codes them */
+int ref_rollout_costs_gains(int K, int T, int A, const float *state_gain, const float *act_gain,
+                            float lambda, const float *x0_in, const float *U_in,
+                            const float *goal_in, const float *w_in, float *eps, float *S_out,
+                            float *xtraj, int nthreads)
+{
+    float state[4] = {state_gain[0], state_gain[1], state_gain[2], state_gain[3]};
+    float act[2] = {act_gain[0], act_gain[1]};
+    return ref_rollout_costs_impl(K, T, A, state, act, lambda, x0_in, U_in, goal_in, w_in, eps,
+                                  S_out, xtraj, nthreads);
+}
+
+static int ref_rollout_costs_impl(int K, int T, int A, float *state, float *act, float lambda,
+                                  const float *x0_in, const float *U_in, const float *goal_in,
+                                  const float *w_in, float *eps, float *S_out, float *xtraj,
+                                  int nthreads)
+{
+    const int S = 2 * A;
 
     std::vector<float> x0(x0_in, x0_in + S), U(U_in, U_in + (size_t)T * A);
     std::vector<float> goal(goal_in, goal_in + S), w(w_in, w_in + S);

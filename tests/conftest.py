@@ -9,7 +9,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["cfgtest", "testcu", "pm1d", "pm2d", "pm3d", "pm3d_ragged"]
+GOLDEN_CASES = ["cfgtest", "testcu", "pm1d", "pm2d", "pm3d", "pm3d_ragged", "pm2d_damped",
+                "pm3d_gains"]
+
+
+def golden_gains(g):
+    """(state_gain, act_gain) of a golden case made with caller-given gains, else None."""
+    return (g["state_gain"], g["act_gain"]) if "state_gain" in g else None
 
 # reference configs (config/point_mass{1,2,3}d.yaml): goal and cost.w per action dim
 REF_CFG = {

@@ -39,7 +39,27 @@ CASES = [
     ("pm2d", 512, 50, 2, 0.1, [1, 0, 0, 0], [1, 1, 50, 50], 0.05, 0.1, 0.025),
     ("pm3d", 512, 50, 3, 0.1, [1, 0.5, 0.75, 0, 0, 0], [1, 1, 1, 5, 5, 5], 0.05, 0.1, 0.025),
     ("pm3d_ragged", 257, 37, 3, 0.05, [1, 0.5, 0.75, 0, 0, 0], [1, 1, 1, 5, 5, 5], 0.2, 0.3, 0.1),
+    # caller-given gains (PointMassModelGpu::init takes them as arguments,
+    # src/point_mass_gpu.cu:25-39): the damped, geared point mass of envs/point_mass2d.xml
+    # (mass 0.5236 + armature 0.01, gear 10, damping 0.1) discretised at dt = 0.1, and a
+    # generic non-trivial set with every gain active
+    ("pm2d_damped", 384, 60, 2, 0.1, [1, 0, 0, 0], [1, 1, 50, 50], 0.05, 0.1, 0.025),
+    ("pm3d_gains", 200, 45, 3, 0.1, [1, 0.5, 0.75, 0, 0, 0], [1, 1, 1, 5, 5, 5], 0.1, 0.2, 0.05),
 ]
+
+
+def damped_gains(dt, mass=0.5236 + 0.01, gear=10.0, damping=0.1):
+    """p' = p + dt v + dt^2/2 a, v' = v + dt a with a = (gear (u+e) - damping v) / mass."""
+    k = damping / mass
+    g = np.array([1.0, dt - 0.5 * dt * dt * k, 0.0, 1.0 - dt * k], np.float32)
+    b = np.array([0.5 * dt * dt * gear / mass, dt * gear / mass], np.float32)
+    return g, b
+
+
+GAINS = {
+    "pm2d_damped": damped_gains(0.1),
+    "pm3d_gains": (np.array([0.98, 0.11, -0.02, 0.93], np.float32), np.array([0.007, 0.12], np.float32)),
+}
 
 
 def main():
@@ -52,14 +72,15 @@ def main():
         goal = np.asarray(goal, np.float32)
         w = np.asarray(w, np.float32)
         small = K * (T + 1) * 2 * A <= 40000
-        out = po.ref_rollout_all(K, T, A, dt, 1.0, x0, U, goal, w, eps, want_traj=small)
+        gains = GAINS.get(name)
+        out = po.ref_rollout_all(K, T, A, dt, 1.0, x0, U, goal, w, eps, want_traj=small, gains=gains)
         S_ref, x_ref = out if small else (out, None)
 
-        p = po.make_problem(K, T, A, dt, goal, w)
+        p = po.make_problem(K, T, A, dt, goal, w, gains=gains)
         S_orc = po.rollout_all(p, x0, U, eps)
         assert np.array_equal(S_orc.view(np.uint32), S_ref.view(np.uint32)), name
         r = po.step(p, x0, U, eps)
-        pf = po.make_problem(K, T, A, dt, goal, w, arith=po.ARITH_FMA)
+        pf = po.make_problem(K, T, A, dt, goal, w, arith=po.ARITH_FMA, gains=gains)
         S_fma = po.rollout_all(pf, x0, U, eps)
         rf = po.step(pf, x0, U, eps)
 
@@ -70,6 +91,8 @@ def main():
                  argmin_fma=rf["argmin"], eta_fma=rf["eta"])
         if small:
             d["x_ref"] = x_ref
+        if gains is not None:
+            d["state_gain"], d["act_gain"] = gains
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **d)
         print(f"{name}: K={K} T={T} A={A} beta={r['beta']:.6f} eta={r['eta']:.6f} "

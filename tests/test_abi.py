@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_layout():
     lib = capi.load()
-    assert lib.mppi_abi_version() == 1
+    assert lib.mppi_abi_version() == 2
     p = capi.MppiParams()
     assert lib.mppi_params_default(C.byref(p)) == 0
     # the C side wrote sizeof(mppi_params): the ctypes mirror must agree
@@ -37,7 +37,7 @@ def test_abi_version_and_struct_layout():
     assert p.lambda_ == 1.0 and p.world_size == 1 and p.comm == capi.COMM_NONE
     assert all(abs(p.sigma[a] - 0.025) < 1e-9 for a in range(capi.MAX_ACT))
     assert all(p.inv_sigma[a] == 1.0 for a in range(capi.MAX_ACT))
-    assert p.flags == 0 and p.seed == 0
+    assert p.flags == 0 and p.seed == 0 and p.model == capi.MODEL_POINT_MASS
 
 
 def test_kernel_names():

@@ -16,7 +16,7 @@ Bars (BASELINE.json north_star):
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, REF_CFG, bits, load_golden, make_inputs
+from conftest import GOLDEN_CASES, REF_CFG, bits, golden_gains, load_golden, make_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -102,7 +102,9 @@ def test_golden_vectors(M, oracle, name):
     g = load_golden(name)
     K, T, A = int(g["K"]), int(g["T"]), int(g["A"])
     for strict in (True, False):
-        ctl = M.PointMassModel(K, T, float(g["dt"]), 2 * A, A, flags=1 if strict else 0)
+        gains = golden_gains(g) or (None, None)
+        ctl = M.PointMassModel(K, T, float(g["dt"]), 2 * A, A, flags=1 if strict else 0,
+                               state_gain=gains[0], act_gain=gains[1])
         ctl.memcpy_set_data(g["x0"], g["U"], g["goal"], g["w"])
         ctl.set_noise(g["eps"])
         na = ctl.get_act()

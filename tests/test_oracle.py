@@ -10,7 +10,7 @@
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, REF_CFG, bits, load_golden, make_inputs
+from conftest import GOLDEN_CASES, REF_CFG, bits, golden_gains, load_golden, make_inputs
 
 
 # ------------------------------------------------------------------ vs oracle/_ref
@@ -52,7 +52,8 @@ def test_oracle_lambda_reaches_ref_cost(oracle):
 def test_oracle_matches_golden(oracle, name):
     g = load_golden(name)
     K, T, A = int(g["K"]), int(g["T"]), int(g["A"])
-    p = oracle.make_problem(K, T, A, float(g["dt"]), g["goal"], g["w"], lam=float(g["lam"]))
+    p = oracle.make_problem(K, T, A, float(g["dt"]), g["goal"], g["w"], lam=float(g["lam"]),
+                            gains=golden_gains(g))
     S, xt = oracle.rollout_all(p, g["x0"], g["U"], g["eps"], want_traj=True)
     assert np.array_equal(bits(S), bits(g["S_ref"]))
     if "x_ref" in g:
@@ -65,8 +66,25 @@ def test_oracle_matches_golden(oracle, name):
     assert np.array_equal(bits(r["U"]), bits(g["U_next"]))
     assert np.array_equal(bits(r["next_act"]), bits(g["next_act"]))
     pf = oracle.make_problem(K, T, A, float(g["dt"]), g["goal"], g["w"], lam=float(g["lam"]),
-                             arith=oracle.ARITH_FMA)
+                             arith=oracle.ARITH_FMA, gains=golden_gains(g))
     assert np.array_equal(bits(oracle.rollout_all(pf, g["x0"], g["U"], g["eps"])), bits(g["S_fma"]))
+
+
+@pytest.mark.parametrize("A,K,T", [(1, 300, 40), (2, 512, 50), (3, 257, 37)])
+def test_oracle_general_gains_match_ref_bit_exact(oracle, A, K, T):
+    """Caller-given gains (the LinearAxis dynamics functor): PointMassModelGpu::init takes the
+    gains as arguments (src/point_mass_gpu.cu:25-39), so the reference's own step() pins them."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    cfg = REF_CFG[A]
+    x0, U, eps = make_inputs(K, T, A, seed=3 * K + A, sigma=0.1)
+    gains = (np.array([0.97, 0.12, 0.03, 0.9], np.float32), np.array([0.02, 0.3], np.float32))
+    ref = oracle.ref_rollout_all(K, T, A, 0.1, 1.0, x0, U, cfg["goal"], cfg["w"], eps,
+                                 want_traj=True, nthreads=4, gains=gains)
+    p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], gains=gains)
+    got = oracle.rollout_all(p, x0, U, eps, want_traj=True, nthreads=4)
+    assert np.array_equal(bits(got[0]), bits(ref[0]))
+    assert np.array_equal(got[1], ref[1])
 
 
 def test_fma_and_strict_agree_to_rounding(oracle):
