@@ -2,6 +2,12 @@
 //
 //   mppi_main -c <config.yaml> [-t traj.csv] [-s step_prefix] [--plant ideal|mjcf] [--steps N] [--samples K]
 //             [--horizon T] [--honour-config] [--seed S] [--devices 0,1,..] [--verify-config] [--quiet]
+//             [--model ideal|mjcf]
+//
+// --model mjcf gives the controller the dynamics of the MJCF body instead of the reference's
+// double integrator (MPPI_MODEL_LINEAR_AXIS: the damped, geared point mass of envs/*.xml
+// discretised at the plant's control period) -- the model-mismatch experiment of the
+// reference's src/model_missmatch.cpp with the mismatch removed.
 //
 // Same sequence as the reference: parse config, build the plant and the controller, get_x,
 // zero action sequence, memcpy_set_data, then loop { get_u; time(get_act); simulate; get_x;
@@ -96,6 +102,7 @@ static void to_csv2(const std::string &filename, const float *x, const float *u,
 int main(int argc, char **argv)
 {
     std::string config_file = "config/point_mass2d.yaml", traj_file, step_file, plant_name = "ideal";
+    std::string model_name = "ideal";
     long max_steps = -1, samples_override = -1, horizon_override = -1;
     bool honour = false, verify = false, quiet = false;
     unsigned long long seed = 0;
@@ -110,6 +117,7 @@ int main(int argc, char **argv)
         else if (a == "-t" || a == "--traj-save") traj_file = next();
         else if (a == "-s" || a == "--step-save") step_file = next();
         else if (a == "--plant") plant_name = next();
+        else if (a == "--model") model_name = next();
         else if (a == "--steps") max_steps = std::stol(next());
         else if (a == "--samples") samples_override = std::stol(next());
         else if (a == "--horizon") horizon_override = std::stol(next());
@@ -152,6 +160,21 @@ int main(int argc, char **argv)
     PointMassModel::Options opt;
     opt.seed = seed;
     if (!devices.empty()) { opt.devices = devices.data(); opt.num_devices = (int)devices.size(); }
+    float state_gain[4], act_gain[2];
+    if (model_name == "mjcf") {
+        // m qdd = gear u - damping qd over one control period h of the mjcf plant (2 x 0.01 s)
+        const double h = 0.02, mass = PointMassEnv::mjcf_mass(), gear = 10.0, damping = 0.1;
+        const double k = damping / mass;
+        state_gain[0] = 1.0f; state_gain[1] = (float)(h - 0.5 * h * h * k);
+        state_gain[2] = 0.0f; state_gain[3] = (float)(1.0 - h * k);
+        act_gain[0] = (float)(0.5 * h * h * gear / mass);
+        act_gain[1] = (float)(h * gear / mass);
+        opt.state_gain = state_gain;
+        opt.act_gain = act_gain;
+    } else if (model_name != "ideal") {
+        std::cerr << "unknown --model " << model_name << std::endl;
+        return 2;
+    }
     if (honour) {
         opt.lambda = cfg.lambda;
         opt.sigma = cfg.noise.data();

@@ -25,8 +25,14 @@ public:
         : A_(act_dim), model_(model), ctrl_dt_(ctrl_dt), sim_end_(sim_end), q_(act_dim, 0.0),
           v_(act_dim, 0.0)
     {
+        mass_ = mjcf_mass();
+    }
+
+    // sphere r = 0.05 of density 1000 + armature 0.01 (envs/point_mass2d.xml:6-10,28-29)
+    static double mjcf_mass()
+    {
         const double kPi = 3.14159265358979323846;
-        mass_ = 1000.0 * 4.0 / 3.0 * kPi * 0.05 * 0.05 * 0.05 + 0.01;   // geom mass + armature
+        return 1000.0 * 4.0 / 3.0 * kPi * 0.05 * 0.05 * 0.05 + 0.01;
     }
 
     // returns true when the episode is over (reference: window closed or time > simend)

@@ -77,6 +77,59 @@ def test_closed_loop_driver(tmp_path, cfg, plant):
 
 
 @pytest.mark.gpu
+def test_driver_with_the_matched_model():
+    """--model mjcf: the controller plans with the MJCF body's own dynamics
+    (MPPI_MODEL_LINEAR_AXIS) instead of the double integrator; the loop runs, the mass moves
+    towards the goal and stays inside the joint range."""
+    _build()
+    r = subprocess.run([BIN, "-c", os.path.join(ROOT, "config", "point_mass2d.yaml"), "--samples",
+                        "20000", "--horizon", "50", "--steps", "300", "--plant", "mjcf", "--model",
+                        "mjcf", "--quiet", "--honour-config"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    final = [float(v) for v in r.stdout.split("final state:")[1].split("\n")[0].split()]
+    assert 0.0 < final[0] <= 1.4 and abs(final[1]) <= 1.4, final
+
+
+@pytest.mark.gpu
+def test_matched_model_predicts_the_mjcf_body():
+    """The gains `mppi_main --model mjcf` passes mean what they say: the controller's predicted
+    trajectories (get_inf tap) follow the exact solution of m q'' = gear u - damping q' under the
+    same piecewise-constant controls, while the reference's double integrator (dt = 0.1, unit
+    gain) is far off -- the reference's model-mismatch experiment (src/model_missmatch.cpp)."""
+    import math
+    import numpy as np
+    import mppi_gpu_b200 as m
+    from conftest import make_inputs
+    K, T, A, h = 64, 50, 2, 0.02
+    mass, gear, damping = 1000.0 * 4.0 / 3.0 * math.pi * 0.05 ** 3 + 0.01, 10.0, 0.1
+    k = damping / mass
+    g = [1.0, h - 0.5 * h * h * k, 0.0, 1.0 - h * k]
+    b = [0.5 * h * h * gear / mass, h * gear / mass]
+    x0, U, eps = make_inputs(K, T, A, seed=4, sigma=0.05, u_scale=0.3)
+    exact = np.zeros((K, T + 1, 2 * A))
+    exact[:, 0] = x0
+    ek = math.exp(-k * h)
+    for t in range(T):
+        u = U[t][None, :].astype(np.float64) + eps[:, t].astype(np.float64)
+        p, v = exact[:, t, :A], exact[:, t, A:]
+        vt = gear * u / damping                          # terminal velocity under this control
+        exact[:, t + 1, A:] = vt + (v - vt) * ek
+        exact[:, t + 1, :A] = p + vt * h + (v - vt) * (1 - ek) / k
+    err = {}
+    for name, kw in (("matched", dict(state_gain=g, act_gain=b)), ("double_integrator", {})):
+        ctl = m.PointMassModel(K, T, 0.1, 2 * A, A, **kw)
+        ctl.memcpy_set_data(x0, U, [1, 0, 0, 0], [1, 1, 50, 50])
+        ctl.set_noise(eps)
+        ctl.get_act()
+        x = ctl.get_inf(want_x=True, want_e=False)["x"].astype(np.float64)
+        ctl.close()
+        err[name] = np.abs(x - exact).max()
+    assert err["matched"] < 2e-3 * np.abs(exact).max() + 1e-4, err
+    assert err["double_integrator"] > 20 * err["matched"], err
+
+
+@pytest.mark.gpu
 def test_step_dump_matches_reference_csv_format_and_reproduces_the_update(tmp_path):
     """-s: the reference's per-step dump (to_csv2, src/main.cu:90-156) that its
     scripts/plot_csv.py consumes; the NumPy recomputation in that script
