@@ -19,6 +19,7 @@
 #include "../../include/mppi_b200.h"
 #include "comm.hpp"
 #include "kernels.cuh"
+#include "finalize.cuh"
 
 using namespace mppi;
 
@@ -64,7 +65,8 @@ struct mppi_handle {
     ProblemDev h_prob{};
     float *h_stage = nullptr;     // pinned [kStageSlots][2*kMaxAct]
     int stage_slot = 0;
-    float *h_next = nullptr;      // pinned [kMaxAct]
+    float *h_next = nullptr;      // pinned + mapped [kNextFloats]: next action, error flag, step seq
+    unsigned long long steps_enqueued = 0;   // == the seq the last enqueued step will publish
 
     CUtensorMap tmap{};        // average kernel: box {256, kAvgTileR}
     CUtensorMap tmap_ro{};     // TMA rollout: box {256, TT*A}
@@ -147,8 +149,6 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
                                           h->d_next, h->p.flags, h->peer_mb, h->p.rank,
                                           h->p.world_size));
         CK(mark());
-        CK(cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * (kMaxAct + 1), cudaMemcpyDeviceToHost,
-                           c.stream));
         CK(mark());
         return MPPI_OK;
     }
@@ -191,9 +191,8 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
     if (!merge_fin && !p2p(h))
         CK(launch_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
                            h->p.flags));
-    // next action (A floats) + the exchange error flag at [kMaxAct]
-    CK(cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * (kMaxAct + 1), cudaMemcpyDeviceToHost,
-                       c.stream));
+    // next action (A floats), the exchange error flag at [kMaxAct] and the step counter are
+    // stored by the finalizing kernel straight into mapped host memory (finalize.cuh)
     CK(mark());
     return MPPI_OK;
 }
@@ -340,7 +339,7 @@ int mppi_destroy(mppi_handle *h)
     if (h->t1) cudaEventDestroy(h->t1);
     cudaFree(h->d_eps); cudaFree(h->d_S); cudaFree(h->d_wt); cudaFree(h->d_acc);
     cudaFree(h->d_U); cudaFree(h->d_Uprev); cudaFree(h->d_part);
-    cudaFree(h->d_next); cudaFree(h->d_prob); cudaFree(h->d_ctl);
+    cudaFree(h->d_prob); cudaFree(h->d_ctl);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_next) cudaFreeHost(h->h_next);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -459,8 +458,6 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     CKH(cudaMalloc(&h->d_acc, sizeof(long long) * ((size_t)h->R + 1)));
     CKH(cudaMalloc(&h->d_U, sizeof(float) * (size_t)h->R));
     CKH(cudaMalloc(&h->d_Uprev, sizeof(float) * (size_t)h->R));
-    CKH(cudaMalloc(&h->d_next, sizeof(float) * 2 * kMaxAct));
-    CKH(cudaMemsetAsync(h->d_next, 0, sizeof(float) * 2 * kMaxAct, h->stream));
     if (p.world_size > 1 && p.comm == MPPI_COMM_P2P) {
         const size_t mb_bytes = sizeof(unsigned long long) * mailbox_slot_words(h->R) * p.world_size;
         CKH(cudaMalloc(&h->d_mailbox, mb_bytes));
@@ -470,7 +467,9 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     CKH(cudaMalloc(&h->d_prob, sizeof(ProblemDev)));
     CKH(cudaMalloc(&h->d_ctl, sizeof(CtlDev)));
     CKH(cudaMallocHost(&h->h_stage, sizeof(float) * kStageSlots * 2 * kMaxAct));
-    CKH(cudaMallocHost(&h->h_next, sizeof(float) * 2 * kMaxAct));
+    CKH(cudaHostAlloc(&h->h_next, sizeof(float) * kNextFloats, cudaHostAllocMapped));
+    memset(h->h_next, 0, sizeof(float) * kNextFloats);
+    CKH(cudaHostGetDevicePointer(&h->d_next, h->h_next, 0));
     // eps zeroed like the reference's cudaMemset(_e, 0) (src/point_mass.cu:69): keeps the
     // pad columns finite and defines injected-noise mode before the first mppi_set_noise.
     CKH(cudaMemsetAsync(h->d_eps, 0, eps_bytes, h->stream));
@@ -709,6 +708,7 @@ int mppi_step_enqueue(mppi_handle *h)
         CK(cudaGraphLaunch(h->graph_exec[which], h->stream));
     }
     h->total_launches += kernels_per_step(h, sample);
+    h->steps_enqueued += 1;
     h->pending = true;
     return MPPI_OK;
 }
@@ -725,7 +725,27 @@ int mppi_step_wait(mppi_handle *h, float *next_act)
     }
     int rc = check_handle(h);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(h->stream));
+    if (h->prof_pending || (h->p.flags & MPPI_FLAG_NO_GRAPH)) {
+        CK(cudaStreamSynchronize(h->stream));
+    } else {
+        // spin on the step counter the finalizing kernel publishes in mapped host memory; look
+        // at the stream now and then so that a failed launch cannot hang the caller
+        volatile unsigned long long *seq =
+            reinterpret_cast<volatile unsigned long long *>(h->h_next + kNextSeqOffset);
+        for (unsigned spins = 0; *seq != h->steps_enqueued; ++spins) {
+            if ((spins & 1023u) == 1023u) {
+                cudaError_t q = cudaStreamQuery(h->stream);
+                if (q != cudaErrorNotReady) {            // finished or failed: settle it the slow way
+                    CK(cudaStreamSynchronize(h->stream));
+                    break;
+                }
+            }
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        if (*seq != h->steps_enqueued)
+            return fail(MPPI_ERR_STATE, "step %llu finished without publishing its result (seq %llu)",
+                        h->steps_enqueued, (unsigned long long)*seq);
+    }
     h->pending = false;
     if (h->prof_pending) {
         // event i+1 closes stage i of {sample, rollout, comm_min, weights, average,

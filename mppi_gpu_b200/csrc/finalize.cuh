@@ -7,6 +7,14 @@ namespace mppi {
 
 // U update + receding-horizon shift from the fixed-point accumulators, executed by ONE CTA
 // (the finalize kernel, or the last CTA of the merged average kernel).  s_u: T*A floats.
+//
+// next_act points into PINNED HOST memory mapped into the device (zero copy): the kernel stores
+// the A floats of the next action and the exchange-error flag straight into the caller's
+// process, then publishes the step counter at next_act + kNextSeqOffset with a system-scope
+// release.  The host spins on that word instead of waiting for a D2H copy node and a stream
+// synchronisation (mppi_step_wait) -- several microseconds of a closed-loop control step.
+constexpr int kNextSeqOffset = 2 * kMaxAct;     // in floats; 8-byte aligned
+constexpr int kNextFloats = 2 * kMaxAct + 2;
 __device__ __forceinline__ void finalize_body(long long *acc, float *__restrict__ U,
                                               float *__restrict__ U_prev,
                                               const ProblemDev *__restrict__ prob, CtlDev *ctl,
@@ -38,15 +46,21 @@ __device__ __forceinline__ void finalize_body(long long *acc, float *__restrict_
         U[i] = v;
         acc[i] = 0;
     }
-    if (threadIdx.x < A) next_act[threadIdx.x] = s_u[threadIdx.x];
+    if (threadIdx.x < 32) {
+        if (threadIdx.x < A) next_act[threadIdx.x] = s_u[threadIdx.x];
+        if (threadIdx.x == A) next_act[kMaxAct] = ctl->comm_error ? 1.0f : 0.0f;   // read with next_act
+        __threadfence_system();
+        __syncwarp();
+    }
     if (threadIdx.x == 0) {
-        next_act[kMaxAct] = ctl->comm_error ? 1.0f : 0.0f;    // read by the host with next_act
         acc[R] = 0;
         ctl->eta = eta;
         ctl->last_key = ctl->min_key;
         ctl->min_key = kMinKeyInit;
-        ctl->step = ctl->step + 1;
+        const unsigned long long step = ctl->step + 1;
+        ctl->step = step;
         ctl->done = 0;
+        st_release_sys_u64(reinterpret_cast<unsigned long long *>(next_act + kNextSeqOffset), step);
     }
 }
 
