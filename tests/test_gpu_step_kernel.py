@@ -189,3 +189,21 @@ def test_auto_chain_picks_by_shard_size(M):
         assert np.array_equal(bits(ref.get_inf(want_e=False)["cost"]), bits(cost))
         assert _close(na, na0, tol=2e-6)
         ref.close()
+
+
+def test_step_kernel_falls_back_when_rows_do_not_fit(M, oracle):
+    """T*A too large for the shared-memory row sums: the flag is accepted and the step runs on
+    the kernel chain (two kernels with injected-free sampled noise: sample is separate -> 3)."""
+    K, T, A = 2000, 700, 4                      # R = 2800 rows: 179 KB of row sums alone
+    cfg = REF_CFG[A]
+    x0, U, _ = make_inputs(K, T, A, seed=13)
+    ctl = M.PointMassModel(K, T, 0.05, 2 * A, A, seed=1, flags=_flags())
+    ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+    na = ctl.get_act()
+    inf = ctl.get_inf()
+    info = ctl.step_info()
+    assert ctl.launch_count() == 3
+    p = oracle.make_problem(K, T, A, 0.05, cfg["goal"], cfg["w"], arith=oracle.ARITH_FMA)
+    ref = oracle.step(p, x0, U, inf["e"])
+    _assert_parity(na, inf, info, ref, K, T, A)
+    ctl.close()
