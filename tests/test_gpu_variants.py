@@ -119,3 +119,4 @@ def test_linear_axis_model_sampled_chains(oracle, flags):
         assert np.allclose(inf["u"].ravel(), ref["U"].ravel(), rtol=1e-5, atol=1e-6)
         assert np.allclose(na, ref["next_act"], rtol=1e-5, atol=1e-6)
     ctl.close()
+
