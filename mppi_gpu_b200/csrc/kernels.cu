@@ -278,8 +278,9 @@ rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long
     constexpr int UST = UStage<A>::kStride;
     constexpr int kRtConsumerWarps = W / 32;
     constexpr uint32_t kTileBytes = ROWS * W * sizeof(float);
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    // declared aligned (TMA destinations need 128 B): no integer round-trip on the address, so
+    // the accesses below stay shared-space LDS/STS instead of generic loads
+    extern __shared__ __align__(1024) uint8_t base[];
     float *s_tile = reinterpret_cast<float *>(base);                          // [stage][ROWS][W]
     float *s_u = s_tile + (size_t)kRtStages * ROWS * W;                     // [T][UST]
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_u + (size_t)T * UST);
@@ -454,9 +455,9 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
                long long *__restrict__ acc, int rows, int nslab, int nchunk, long long k_local,
                const ProblemDev *__restrict__ prob, CtlDev *__restrict__ ctl, FinalizeArgs fin)
 {
-    extern __shared__ uint8_t smem_raw[];
-    // 128-byte aligned carve-up (TMA destinations need 128 B)
-    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    // declared aligned (TMA destinations need 128 B): no integer round-trip on the address, so
+    // the accesses below stay shared-space LDS/STS instead of generic loads
+    extern __shared__ __align__(1024) uint8_t base[];
     float *s_tile = reinterpret_cast<float *>(base);                               // [stage][R][K]
     float *s_wt   = s_tile + (size_t)kAvgStages * kAvgTileR * kAvgTileK;           // [stage][K]
     float *s_row  = s_wt + (size_t)kAvgStages * kAvgTileK;                         // [rows32]

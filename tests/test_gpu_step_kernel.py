@@ -207,3 +207,48 @@ def test_step_kernel_falls_back_when_rows_do_not_fit(M, oracle):
     ref = oracle.step(p, x0, U, inf["e"])
     _assert_parity(na, inf, info, ref, K, T, A)
     ctl.close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes_every_chain_agrees(M, oracle, seed):
+    """Random (K, T, A, lambda, sigma, arithmetic, model) per seed: the three chains of the same
+    controller draw the same noise; the oracle on each chain's noise and U confirms costs bit
+    for bit and eta / weights / U within 1e-5."""
+    from mppi_gpu_b200 import capi
+    rs = np.random.RandomState(1000 + seed)
+    A = int(rs.randint(1, 5))
+    T = int(rs.randint(1, 90))
+    K = int(rs.choice([rs.randint(1, 300), rs.randint(300, 5000), rs.randint(5000, 60000)]))
+    lam = float(rs.choice([0.05, 0.5, 1.0, 7.0]))
+    sigma = float(rs.choice([0.01, 0.025, 0.3]))
+    strict = bool(rs.randint(0, 2))
+    gains = None
+    if rs.randint(0, 2):
+        gains = (np.array([1.0, 0.1, rs.uniform(-0.05, 0.05), rs.uniform(0.85, 1.0)], np.float32),
+                 np.array([rs.uniform(0.0, 0.02), rs.uniform(0.05, 0.3)], np.float32))
+    cfg = REF_CFG[A]
+    x0, U, _ = make_inputs(K, T, A, seed=seed)
+    base = capi.FLAG_STRICT_ARITH if strict else 0
+    kw = dict(seed=seed, lam=lam, sigma=sigma)
+    if gains is not None:
+        kw.update(state_gain=gains[0], act_gain=gains[1])
+    p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], lam=lam, gains=gains,
+                            arith=oracle.ARITH_STRICT if strict else oracle.ARITH_FMA)
+    first = None
+    for chain in (capi.FLAG_STEP_KERNEL, capi.FLAG_FUSED_SAMPLING, 0):
+        ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, flags=base | chain, **kw)
+        ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+        ctl.get_act()                                   # step 0
+        pre = ctl.get_u()
+        na = ctl.get_act()                              # step 1, from the updated U
+        inf, info = ctl.get_inf(), ctl.step_info()
+        ctl.close()
+        # U of step 0 agrees between chains to rounding only, so every chain's step 1 is checked
+        # through the oracle run from that chain's own U
+        ref = oracle.step(p, x0, pre, inf["e"])
+        _assert_parity(na, inf, info, ref, K, T, A)
+        if first is None:
+            first = (pre, inf["e"])
+        else:
+            assert np.array_equal(bits(inf["e"]), bits(first[1]))
+            assert _close(pre, first[0], tol=2e-6)
