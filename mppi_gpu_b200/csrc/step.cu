@@ -58,7 +58,6 @@ constexpr int kStTileR     = 40;    // eps rows per TMA box
 constexpr int kStMaxStages = 8;     // boxes in flight per SM (8 x 20 KB): two per consumer warp;
                                     // 4 (one per consumer warp) when shared memory is short
 constexpr int kStConsumers = 4;     // consumer warps
-constexpr int kStMergeGroups = 8;   // CTA groups of the final merge
 
 struct StepSmemLayout {
     size_t tile, wt, part, u, scale, bars, done, misc, total;
@@ -78,15 +77,16 @@ __host__ __device__ inline StepSmemLayout step_smem_layout(int T, int A, long lo
     l.scale = o; o += (size_t)kStMaxStages * sizeof(float);
     l.bars  = o; o += (size_t)2 * kStMaxStages * sizeof(uint64_t);
     l.done  = o; o += (size_t)((list_len + 3) / 4 * 4) * sizeof(unsigned int);
-    l.misc  = o; o += 32;
+    l.misc  = o; o += 32;                            // {ref, eta, last, next} + the merge mbarrier
     l.total = o;
     return l;
 }
 
-// the merge of the per-CTA records reuses the tile ring: [groups][R+1] doubles + [grid] floats
+// the merge of the per-CTA records reuses the ring / row-sum / U region: merged sums, U_new, the
+// rescale factors and at least eight records per bulk-copy pass
 __host__ __device__ inline size_t step_merge_bytes(int R, int grid)
 {
-    return (size_t)kStMergeGroups * (R + 8) * sizeof(double) + (size_t)(grid + R) * sizeof(float) + 64;
+    return (size_t)(R + 1) * 8 + (size_t)(R + grid) * 4 + 128 + (size_t)8 * ((R + 2 + 3) & ~3) * 4;
 }
 
 #ifdef MPPI_STEP_TRACE
@@ -389,6 +389,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
     if (threadIdx.x == 0) { rec[R] = s_misc[1]; rec[R + 1] = s_misc[0]; }
 
     __threadfence();                       // the record and the min key before the ticket
+    fence_proxy_async_all();               // ... and before the last CTA's bulk copy of the records
     named_bar_sync(1, kEpiThreads);
     if (threadIdx.x == 0) {
         STEP_TRACE(202);
@@ -398,7 +399,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
     }
     named_bar_sync(1, kEpiThreads);
     if (*s_last) {
-        // ---- merge the records (fixed order: CTA groups, then CTAs inside a group), then part 5
+        // ---- merge the records in CTA order (deterministic), then part 5
         __threadfence();
 #ifdef MPPI_STEP_TRACE
         if (threadIdx.x == 0) { g_step_trace_all[0][5] = gtimer(); g_step_trace_all[0][7] = blockIdx.x; }
@@ -407,54 +408,67 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
         const unsigned long long mk = *reinterpret_cast<volatile unsigned long long *>(&ctl->min_key);
         const float beta = ordered_to_float((uint32_t)(mk >> 32));
         const int nc = (int)gridDim.x;
-        const int ncol = rstride / 4;                                   // float4 columns of a record
-        double *s_m = reinterpret_cast<double *>(base + L.tile);        // [groups][rstride]
-        float *s_f = reinterpret_cast<float *>(s_m + (size_t)kStMergeGroups * rstride);   // [grid]
-        float *s_unew = s_f + nc;                                       // [R]
-        for (int c = threadIdx.x; c < nc; c += kEpiThreads) {
-            const float ref_c = __ldcg(part + (size_t)c * rstride + R + 1);
-            s_f[c] = expf(__fmul_rn(nil, __fsub_rn(ref_c, beta)));     // ref_c = +inf -> 0
+        // The ring, the row sums and the U staging are free now: the records are pulled into
+        // that region with ONE bulk copy per pass (as many records as fit) instead of strided
+        // L2 loads with a handful in flight per thread, and merged from shared memory.
+        constexpr int kMaxOut = 4;                                      // outputs per thread (R+1 <= 2048)
+        const size_t cap = L.scale;                                     // bytes of reusable shared memory
+        long long *s_acc = reinterpret_cast<long long *>(base);         // [R+1] merged, fixed point
+        float *s_unew = reinterpret_cast<float *>(s_acc + (R + 1));     // [R]
+        float *s_f = s_unew + R;                                        // [per pass]
+        const size_t rec_off = (((size_t)(R + 1) * 8 + (size_t)R * 4 + (size_t)nc * 4) + 127) & ~(size_t)127;
+        float *s_rec = reinterpret_cast<float *>(base + rec_off);       // [per pass][rstride]
+        const int per = (int)((cap - rec_off) / ((size_t)rstride * sizeof(float)));
+        uint64_t *mbar = reinterpret_cast<uint64_t *>(s_misc + 4);      // 8-byte aligned, unused so far
+        if (threadIdx.x == 0) {
+            mbar_init(mbar, 1);
+            fence_mbar_init();
         }
-        named_bar_sync(1, kEpiThreads);
-        const int per = (nc + kStMergeGroups - 1) / kStMergeGroups;
-        for (int it = threadIdx.x; it < kStMergeGroups * ncol; it += kEpiThreads) {
-            const int gq = it / ncol, col = it - gq * ncol;
-            const float4 *src = reinterpret_cast<const float4 *>(part) + col;
-            const int c0 = gq * per, c1 = min(nc, c0 + per);
-            double sx = 0.0, sy = 0.0, sz = 0.0, sw = 0.0;
-            for (int cb = c0; cb < c1; cb += 5) {                       // 5 x 16 B in flight, fixed order
-                float4 v[5];
+        double sum[kMaxOut];
 #pragma unroll
-                for (int j = 0; j < 5; ++j)
-                    v[j] = cb + j < c1 ? __ldcg(src + (size_t)(cb + j) * ncol)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < 5; ++j)
-                    if (cb + j < c1) {
-                        const double f = (double)s_f[cb + j];
-                        sx += (double)v[j].x * f; sy += (double)v[j].y * f;
-                        sz += (double)v[j].z * f; sw += (double)v[j].w * f;
-                    }
+        for (int o = 0; o < kMaxOut; ++o) sum[o] = 0.0;
+        uint32_t parity = 0;
+        for (int c0 = 0; c0 < nc; c0 += per, parity ^= 1) {
+            const int n = min(per, nc - c0);
+            named_bar_sync(1, kEpiThreads);                             // region free, barrier initialised
+            if (threadIdx.x == 0) {
+                fence_proxy_async_all();                                // generic accesses above -> async copy
+                const uint32_t bytes = (uint32_t)((size_t)n * rstride * sizeof(float));
+                mbar_arrive_expect_tx(mbar, bytes);
+                bulk_load_1d(s_rec, part + (size_t)c0 * rstride, bytes, mbar);
             }
-            double *dst = s_m + (size_t)gq * rstride + 4 * col;
-            dst[0] = sx; dst[1] = sy; dst[2] = sz; dst[3] = sw;
+            mbar_wait(mbar, parity);
+            for (int c = threadIdx.x; c < n; c += kEpiThreads)
+                s_f[c] = expf(__fmul_rn(nil, __fsub_rn(s_rec[(size_t)c * rstride + R + 1], beta)));   // +inf -> 0
+            named_bar_sync(1, kEpiThreads);
+#pragma unroll
+            for (int o = 0; o < kMaxOut; ++o) {
+                const int i = threadIdx.x + o * kEpiThreads;            // i == R: eta
+                if (i <= R) {
+                    double a = sum[o];
+                    for (int c = 0; c < n; ++c)                         // fixed order: CTA 0, 1, 2, ...
+                        a += (double)s_rec[(size_t)c * rstride + i] * (double)s_f[c];
+                    sum[o] = a;
+                }
+            }
         }
         named_bar_sync(1, kEpiThreads);
-        for (int i = threadIdx.x; i <= R; i += kEpiThreads) {           // i == R: eta
-            double s = 0.0;
 #pragma unroll
-            for (int gq = 0; gq < kStMergeGroups; ++gq) s += s_m[(size_t)gq * rstride + i];
-            acc[i] = __double2ll_rn(s * kAccScale);
+        for (int o = 0; o < kMaxOut; ++o) {
+            const int i = threadIdx.x + o * kEpiThreads;
+            if (i <= R) {
+                const long long q = __double2ll_rn(sum[o] * kAccScale);
+                if (do_finalize) s_acc[i] = q;                          // stays on chip
+                else             acc[i] = q;                            // K-shard: cross-GPU merge kernel next
+            }
         }
         if (!do_finalize) {
-            // K-shard: the accumulators (relative to this shard's minimum, which stays in
-            // ctl->min_key) go through the cross-GPU merge kernel next
+            // the accumulators are relative to this shard's minimum, which stays in ctl->min_key
             if (threadIdx.x == 0) ctl->done = 0;
             return;
         }
-        __threadfence();
         named_bar_sync(1, kEpiThreads);
-        finalize_body(acc, fin.U, fin.U_prev, prob, ctl, fin.next_act, fin.T, fin.A, fin.flags,
+        finalize_body(s_acc, fin.U, fin.U_prev, prob, ctl, fin.next_act, fin.T, fin.A, fin.flags,
                       s_unew, kEpiThreads, 1);
 #ifdef MPPI_STEP_TRACE
         if (threadIdx.x == 0) { g_step_trace[0][203] = gtimer(); g_step_trace_all[0][6] = gtimer(); }
@@ -505,8 +519,8 @@ StepGeom step_geom(int T, int A, long long k_pad, int num_sms)
     g.nstages = 0;
     for (int ns = kStMaxStages; ns >= kStConsumers; ns -= kStConsumers) {
         const size_t b = step_smem_layout(T, A, g.list_len, ns).total;
-        if (b <= kStepSmemMax &&
-            step_merge_bytes(T * A, g.grid) <= (size_t)ns * kStTileR * kStTileK * sizeof(float)) {
+        if (b <= kStepSmemMax && T * A + 1 <= 4 * (kStepNR + 1) * 32 &&
+            step_merge_bytes(T * A, g.grid) <= step_smem_layout(T, A, g.list_len, ns).scale) {
             g.nstages = ns;
             g.smem = b;
             break;
@@ -515,7 +529,7 @@ StepGeom step_geom(int T, int A, long long k_pad, int num_sms)
     if (const char *env = getenv("MPPI_STEP_STAGES")) {
         const int v = atoi(env);
         if (v >= kStConsumers && v % kStConsumers == 0 && v <= g.nstages &&
-            step_merge_bytes(T * A, g.grid) <= (size_t)v * kStTileR * kStTileK * sizeof(float)) {
+            step_merge_bytes(T * A, g.grid) <= step_smem_layout(T, A, g.list_len, v).scale) {
             g.nstages = v;
             g.smem = step_smem_layout(T, A, g.list_len, v).total;
         }
