@@ -177,7 +177,9 @@ int mppi_set_problem(mppi_handle *h, const float *x0, const float *u, const floa
 int mppi_set_state(mppi_handle *h, const float *x);
 
 /* == get_act(next_act) (src/point_mass.cu:129-203): one control step; writes the
- * A floats of U[0,:] *before* the shift; U is left already shifted. Blocking. */
+ * A floats of U[0,:] *before* the shift; U is left already shifted. Blocking: the
+ * finalizing kernel stores the action and the step counter into pinned host memory
+ * mapped into the device, and the call returns as soon as that counter shows up. */
 int mppi_step(mppi_handle *h, float *next_act);
 
 /* The two halves of mppi_step for callers that overlap host work: enqueue the
