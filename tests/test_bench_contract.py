@@ -44,3 +44,27 @@ def test_product_arm_needs_a_gpu():
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0
     assert "no CUDA device" in (r.stdout + r.stderr)
+
+
+@pytest.mark.gpu
+def test_product_arm_prints_contract_line():
+    """One short run of the product arm on the GPU: the JSON line carries every key of the
+    bench contract (value, e2e with host<->device bytes, roofline, cpu_baseline, clocks,
+    gpu_launches) and names the workload."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3",
+                        "--workload", "point_mass2d_K1e5_T200"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["metric"] == "rollout_steps_per_s" and d["unit"] == "rollout-steps/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["gpu_launches"] >= 5 and "workload" in d["config"]
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 16 and d["e2e"]["d2h_bytes_per_step"] == 8
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] > 0
+    assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
+    assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["scaling"] == "strong"
