@@ -595,8 +595,16 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
         }
     }
     __syncthreads();
-    if (t_end > t_begin)
-        for (int r = threadIdx.x; r < rows; r += blockDim.x) acc_add(acc + r, s_row[r]);
+    if (t_end > t_begin) {
+        // only the row chunks this CTA's tiles touched: with few tiles per CTA (small K) the
+        // other rows would be 64-bit atomics that add zero, all contending for the same words
+        const long long n = t_end - t_begin;
+        const int c_first = (int)(t_begin % nchunk);
+        for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+            const int chunk = r / kAvgTileR;
+            if (n >= nchunk || (chunk - c_first + nchunk) % nchunk < n) acc_add(acc + r, s_row[r]);
+        }
+    }
 
     if (MERGE_FIN) {
         __threadfence();                       // this CTA's atomics before its ticket
