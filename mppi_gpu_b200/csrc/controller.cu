@@ -360,8 +360,8 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     if (p.state_dim != 2 * p.act_dim)
         return fail(MPPI_ERR_INVALID, "state_dim %d must be 2*act_dim (point mass: positions, velocities)",
                     p.state_dim);
-    if (p.samples < 1 || p.samples > 0xffffffffll)
-        return fail(MPPI_ERR_INVALID, "samples %lld out of range", (long long)p.samples);
+    if (p.samples < 1 || p.samples > 0x7fffff00ll)       // TMA box coordinates are int32 sample indices
+        return fail(MPPI_ERR_INVALID, "samples %lld out of range [1, 2^31-256]", (long long)p.samples);
     if (p.horizon < 1 || (long long)p.horizon * p.act_dim > 32768)
         return fail(MPPI_ERR_INVALID, "horizon %d out of range", p.horizon);
     if (!(p.lambda > 0.0f)) return fail(MPPI_ERR_INVALID, "lambda must be > 0");

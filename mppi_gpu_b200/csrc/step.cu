@@ -517,6 +517,7 @@ StepGeom step_geom(int T, int A, long long k_pad, int num_sms)
     g.grid = (int)(g.ntiles < num_sms ? g.ntiles : num_sms);
     g.list_len = (g.ntiles + g.grid - 1) / g.grid;
     g.nstages = 0;
+    if (k_pad >= (1ll << 31)) return g;             // TMA box coordinates are int32 sample indices
     for (int ns = kStMaxStages; ns >= kStConsumers; ns -= kStConsumers) {
         const size_t b = step_smem_layout(T, A, g.list_len, ns).total;
         if (b <= kStepSmemMax && T * A + 1 <= 4 * (kStepNR + 1) * 32 &&
