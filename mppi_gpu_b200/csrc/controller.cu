@@ -4,7 +4,9 @@
 // src/point_mass.cu:19-491): owns every device buffer of one K-shard, builds the control
 // step as a CUDA graph once and replays it per step.  Where the reference issues ~3T+8
 // launches and as many cudaDeviceSynchronize() per get_act (src/point_mass.cu:129-203,
-// :384-480), one step here is one cudaGraphLaunch of 5 kernels + a 4A-byte D2H copy node.
+// :384-480), one step here is one cudaGraphLaunch of 1-3 kernels (step kernel / fused chain /
+// unfused chain, plus one exchange kernel on K-shards); the finalizing kernel publishes the next
+// action and the step counter in mapped host memory, so the graph holds no copy node.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>

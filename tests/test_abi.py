@@ -106,3 +106,19 @@ def test_product_does_not_touch_the_oracle():
                         if hits:
                             bad.append((os.path.join(dp, f), hits))
     assert not bad, bad
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/mppi_b200.h is what a cgo / FFI / C caller binds: it must compile as strict C99
+    and a C program must link against the library without any C++ or CUDA header."""
+    import subprocess
+    src = tmp_path / "bind.c"
+    src.write_text('#include "mppi_b200.h"\n'
+                   "int main(void) { mppi_params p; if (mppi_params_default(&p)) return 2;\n"
+                   "  return (p.struct_size == sizeof p && mppi_abi_version() == MPPI_ABI_VERSION) ? 0 : 1; }\n")
+    exe = tmp_path / "bind"
+    libdir = os.path.join(ROOT, "mppi_gpu_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", str(src),
+                    "-I", os.path.join(ROOT, "include"), "-L", libdir, "-lmppi_b200",
+                    f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
