@@ -327,6 +327,9 @@ def run_ours(args, name, K, T, A, dt, goal, w):
                              if one_kernel else
                              "sample+rollout(fused) -> weights -> average -> finalize"
                              if flags & capi.FLAG_FUSED_SAMPLING else
+                             "rollout -> weights -> average -> finalize; the sampler of step n+1 runs "
+                             "behind step n's chain on a second stream (pipelined sampling)"
+                             if flags & capi.FLAG_PIPELINED_SAMPLING else
                              "sample -> rollout -> weights -> average -> finalize"),
                    "timing": "value: CUDA events on the controller stream around K graph launches; "
                              "kernels/roofline: CUDA events between kernels in a second region of K steps"},
@@ -423,7 +426,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--flags", type=int, default=-1,
                     help="MPPI_FLAG_* bits; default MPPI_FLAG_AUTO_CHAIN: >= 4e5 samples/GPU the one-kernel "
-                         "step (128), >= 1.2e5 fused sampling (32), else the unfused chain")
+                         "step (128), >= 1.2e5 fused sampling (32), else the unfused chain with pipelined "
+                         "sampling (512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="K-shard exchange for --gpus > 1: NVLink peer mailboxes or NCCL")

@@ -2,7 +2,10 @@
 //
 //   mppi_main -c <config.yaml> [-t traj.csv] [-s step_prefix] [--plant ideal|mjcf] [--steps N] [--samples K]
 //             [--horizon T] [--honour-config] [--seed S] [--devices 0,1,..] [--verify-config] [--quiet]
-//             [--model ideal|mjcf]
+//             [--model ideal|mjcf] [--plant-us N] [--flags BITS [--exact-flags]]
+//
+// --plant-us N makes the plant's turn take N microseconds of host time (the reference steps
+// MuJoCo there); --flags adds MPPI_FLAG_* bits to the default MPPI_FLAG_AUTO_CHAIN.
 //
 // --model mjcf gives the controller the dynamics of the MJCF body instead of the reference's
 // double integrator (MPPI_MODEL_LINEAR_AXIS: the damped, geared point mass of envs/*.xml
@@ -106,6 +109,9 @@ int main(int argc, char **argv)
     long max_steps = -1, samples_override = -1, horizon_override = -1;
     bool honour = false, verify = false, quiet = false;
     unsigned long long seed = 0;
+    long plant_us = 0;             // emulated compute time of the plant's step (busy wait)
+    unsigned extra_flags = 0;      // MPPI_FLAG_* bits on top of the default (auto chain)
+    bool exact_flags = false;
     std::vector<int> devices;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -122,6 +128,9 @@ int main(int argc, char **argv)
         else if (a == "--samples") samples_override = std::stol(next());
         else if (a == "--horizon") horizon_override = std::stol(next());
         else if (a == "--seed") seed = std::stoull(next());
+        else if (a == "--plant-us") plant_us = std::stol(next());
+        else if (a == "--flags") extra_flags = (unsigned)std::stoul(next(), nullptr, 0);
+        else if (a == "--exact-flags") exact_flags = true;   // --flags replaces the default
         else if (a == "--devices") {           // e.g. --devices 0,1,2,3 : K sharded over GPUs
             std::string list = next();
             size_t pos = 0;
@@ -159,6 +168,7 @@ int main(int argc, char **argv)
 
     PointMassModel::Options opt;
     opt.seed = seed;
+    opt.flags = exact_flags ? extra_flags : (opt.flags | extra_flags);
     if (!devices.empty()) { opt.devices = devices.data(); opt.num_devices = (int)devices.size(); }
     float state_gain[4], act_gain[2];
     if (model_name == "mjcf") {
@@ -202,6 +212,12 @@ int main(int argc, char **argv)
             std::cout << std::endl;
         }
         done = env.simulate(next_act.data());
+        if (plant_us > 0) {
+            // a real plant (the reference steps MuJoCo here, src/main.cu:335-337) takes time:
+            // emulate it, so that latency is measured as a closed loop sees it
+            const auto until = Clock::now() + std::chrono::microseconds(plant_us);
+            while (Clock::now() < until) { }
+        }
         env.get_x(init_state.data());
         u.push_back(next_act);
         x.push_back(init_state);

@@ -76,7 +76,22 @@ extern "C" {
                                                >= 4e5 samples: MPPI_FLAG_STEP_KERNEL (single
                                                shard or MPPI_COMM_P2P), >= 1.2e5:
                                                MPPI_FLAG_FUSED_SAMPLING, else the unfused
-                                               chain.  mppi_get_flags returns the choice.     */
+                                               chain with MPPI_FLAG_PIPELINED_SAMPLING.
+                                               mppi_get_flags returns the choice.             */
+
+#define MPPI_FLAG_PIPELINED_SAMPLING (1u << 9) /* unfused chain only, a LATENCY option for closed
+                                               loops: as soon as step n has published its action
+                                               the noise of step n+1 is drawn (second stream,
+                                               second eps buffer) while the caller's plant has
+                                               its turn, so that mppi_step(n+1) is rollout +
+                                               average only.  Philox is counter based: eps
+                                               depends on (seed, step, k, t, a), not on U or x.
+                                               Same noise, same results, bit for bit; throughput
+                                               of back-to-back steps is unchanged.  Costs a
+                                               second eps buffer; ignored with fused sampling,
+                                               the step kernel, injected noise,
+                                               MPPI_FLAG_NO_GRAPH and profiling (those steps run
+                                               the plain chain)                               */
 
 /* mppi_params.comm */
 #define MPPI_COMM_NONE  0   /* single shard                                          */

@@ -29,6 +29,7 @@ FLAG_FUSED_SAMPLING = 1 << 5
 FLAG_SPLIT_KERNELS = 1 << 6
 FLAG_STEP_KERNEL = 1 << 7
 FLAG_AUTO_CHAIN = 1 << 8
+FLAG_PIPELINED_SAMPLING = 1 << 9
 
 COMM_NONE, COMM_NCCL, COMM_P2P = 0, 1, 2
 MODEL_POINT_MASS, MODEL_LINEAR_AXIS = 0, 1

@@ -75,6 +75,20 @@ struct mppi_handle {
     CUtensorMap tmap_st{};     // step kernel: box {128, 40}
     float *d_part = nullptr;   // step kernel: one {ref, eta, row sums} record per CTA
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // [0] sampling, [1] injected noise
+
+    // MPPI_FLAG_PIPELINED_SAMPLING: a second eps buffer with its tensor maps; d_eps / tmap /
+    // tmap_ro are always the buffer the NEXT chain reads, the pairs are swapped after every
+    // pipelined step.  graph_pipe[i]: the sampler-less chain on base buffer i.  The sampler of
+    // the step after runs on stream2, behind the chain, ordered against it by two events.
+    float *d_eps_alt = nullptr;
+    float *eps_base[2] = {nullptr, nullptr};
+    CUtensorMap tmap_alt{}, tmap_ro_alt{};
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_sampled = nullptr;      // stream2: the noise drawn ahead is complete
+    cudaEvent_t ev_chain_done = nullptr;   // stream: the last chain has finished reading its buffer
+    cudaGraphExec_t graph_pipe[2] = {nullptr, nullptr};
+    bool presampled = false;   // d_eps holds (or is receiving) the noise of the next step,
+                               // d_eps_alt the noise the last step consumed
     NcclComm comm;
     unsigned long long *d_mailbox = nullptr;              // MPPI_COMM_P2P: this rank's mailbox
     unsigned long long *peer_mb[kMaxWorld] = {};          // every rank's mailbox mapped here
@@ -107,7 +121,15 @@ bool one_kernel(const mppi_handle *h, bool sample)
            !(h->p.flags & MPPI_FLAG_SPLIT_KERNELS) && h->d_part != nullptr;
 }
 
-int encode_tmap(mppi_handle *h, CUtensorMap *out, int box_cols, int box_rows)
+// pipelined sampling applies to the sampled, unfused, graph-replayed chain only
+bool pipelined(const mppi_handle *h, bool sample)
+{
+    return sample && h->d_eps_alt != nullptr && !h->profiling && !(h->p.flags & MPPI_FLAG_NO_GRAPH);
+}
+// the noise the last finished step consumed (get_inf tap)
+float *last_eps(const mppi_handle *h) { return h->presampled ? h->d_eps_alt : h->d_eps; }
+
+int encode_tmap(mppi_handle *h, CUtensorMap *out, int box_cols, int box_rows, float *base = nullptr)
 {
     typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                     const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -123,7 +145,7 @@ int encode_tmap(mppi_handle *h, CUtensorMap *out, int box_cols, int box_rows)
     const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = reinterpret_cast<EncodeTiled>(fn)(
-        out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->d_eps, gdim, gstride, box, estr,
+        out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base ? base : h->d_eps, gdim, gstride, box, estr,
         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MPPI_ERR_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
@@ -221,6 +243,28 @@ int build_graph(mppi_handle *h, int which)
     e = cudaGraphInstantiate(&h->graph_exec[which], g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+    return MPPI_OK;
+}
+
+// The sampler-less chain (== the chain of the injected-noise mode) on the current buffer.
+int build_pipe_graph(mppi_handle *h, int which)
+{
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_chain(h, false, nullptr);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    if (rc != MPPI_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "cudaStreamEndCapture -> %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->graph_pipe[which], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(MPPI_ERR_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+    return MPPI_OK;
+}
+
+// noise drawn ahead may still be landing in d_eps: wait before anything else touches it
+int quiesce_side(mppi_handle *h)
+{
+    if (h->stream2 && h->presampled) CK(cudaStreamSynchronize(h->stream2));
     return MPPI_OK;
 }
 
@@ -336,6 +380,13 @@ int mppi_destroy(mppi_handle *h)
             cudaIpcCloseMemHandle(h->peer_mb[r]);
     cudaFree(h->d_mailbox);
     for (auto &g : h->graph_exec) if (g) cudaGraphExecDestroy(g);
+    for (auto &g : h->graph_pipe) if (g) cudaGraphExecDestroy(g);
+    if (h->stream2) cudaStreamSynchronize(h->stream2);
+    if (h->ev_sampled) cudaEventDestroy(h->ev_sampled);
+    if (h->ev_chain_done) cudaEventDestroy(h->ev_chain_done);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    // d_eps / d_eps_alt swap roles every pipelined step: free by base pointer
+    if (h->eps_base[1]) { cudaFree(h->eps_base[1]); h->d_eps = h->eps_base[0]; }
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
@@ -451,7 +502,13 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
         }                                                                                 \
     } while (0)
 
-    CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {
+        // the step's critical path outranks the sampler that runs ahead on stream2 (kernel
+        // nodes inherit the priority of the stream they were captured on)
+        int least = 0, greatest = 0;
+        CKH(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CKH(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, greatest));
+    }
     c.stream = h->stream;
     const size_t eps_bytes = sizeof(float) * (size_t)h->R * (size_t)c.k_pad;
     CKH(cudaMalloc(&h->d_eps, eps_bytes));
@@ -493,8 +550,24 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
         if (!(p.flags & MPPI_FLAG_SPLIT_KERNELS)) {
             if (c.k_local >= 400000 && can_step) h->p.flags |= MPPI_FLAG_STEP_KERNEL;
             else if (c.k_local >= 120000)        h->p.flags |= MPPI_FLAG_FUSED_SAMPLING;
+            // the unfused chain of a closed loop draws the next step's noise during the plant's
+            // turn: get_act is 3-28 % shorter for any plant time (K=1e5: 103 -> 100 us with an
+            // instantaneous plant, 74 us once the plant takes 40 us)
+            else                                 h->p.flags |= MPPI_FLAG_PIPELINED_SAMPLING;
         }
         h->p.flags &= ~MPPI_FLAG_AUTO_CHAIN;
+    }
+    if ((h->p.flags & MPPI_FLAG_PIPELINED_SAMPLING) &&
+        !(h->p.flags & (MPPI_FLAG_FUSED_SAMPLING | MPPI_FLAG_STEP_KERNEL))) {
+        int least = 0, greatest = 0;
+        CKH(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CKH(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, least));
+        CKH(cudaEventCreateWithFlags(&h->ev_sampled, cudaEventDisableTiming));
+        CKH(cudaEventCreateWithFlags(&h->ev_chain_done, cudaEventDisableTiming));
+        CKH(cudaMalloc(&h->d_eps_alt, eps_bytes));
+        h->eps_base[0] = h->d_eps;
+        h->eps_base[1] = h->d_eps_alt;
+        CKH(cudaMemsetAsync(h->d_eps_alt, 0, eps_bytes, h->stream));
     }
     if ((h->p.flags & MPPI_FLAG_STEP_KERNEL) && step_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms)) {
         CKH(configure_step(c));
@@ -528,6 +601,10 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     if ((rc = encode_tmap(h, &h->tmap, kAvgTileK, kAvgTileR)) != MPPI_OK) { mppi_destroy(h); return rc; }
     if ((rc = encode_tmap(h, &h->tmap_st, kStepTileK, kStepTileR)) != MPPI_OK) { mppi_destroy(h); return rc; }
     if ((rc = encode_tmap(h, &h->tmap_ro, c.rollout_tma_width, rollout_tma_rows(p.act_dim))) != MPPI_OK) { mppi_destroy(h); return rc; }
+    if (h->d_eps_alt) {
+        if ((rc = encode_tmap(h, &h->tmap_alt, kAvgTileK, kAvgTileR, h->d_eps_alt)) != MPPI_OK) { mppi_destroy(h); return rc; }
+        if ((rc = encode_tmap(h, &h->tmap_ro_alt, c.rollout_tma_width, rollout_tma_rows(p.act_dim), h->d_eps_alt)) != MPPI_OK) { mppi_destroy(h); return rc; }
+    }
 
     if (multi(h) && p.comm == MPPI_COMM_NCCL) {
         std::string err;
@@ -701,6 +778,44 @@ int mppi_step_enqueue(mppi_handle *h)
         return fail(MPPI_ERR_STATE, "mppi_step before mppi_comm_p2p_connect");
     const bool sample = !h->injected;
     const int which = sample ? 0 : 1;
+    if (pipelined(h, sample)) {
+        // step n: the chain reads d_eps, which the sampler filled after step n-1 had published
+        // its action -- during the plant's turn; the sampler of step n+1 is queued behind this
+        // step's chain on stream2 and fills d_eps_alt (two buffers so that get_inf still
+        // returns the noise the last step consumed).  Queued BEHIND the chain, not beside it:
+        // run side by side the sampler takes from the chain exactly what it saves (measured,
+        // DESIGN.md section 4c), so the gain is latency, not throughput.
+        if (!h->presampled) {
+            // first pipelined step, or the first after a step of another kind: draw in line
+            CK(launch_sample(h->ctx, h->d_eps, h->d_ctl, false, 0));
+            h->total_launches += 1;
+        } else {
+            CK(cudaStreamWaitEvent(h->stream, h->ev_sampled, 0));
+        }
+        const int base = h->d_eps == h->eps_base[0] ? 0 : 1;
+        if (!h->graph_pipe[base] && (rc = build_pipe_graph(h, base)) != MPPI_OK) return rc;
+        CK(cudaGraphLaunch(h->graph_pipe[base], h->stream));
+        CK(cudaEventRecord(h->ev_chain_done, h->stream));
+        // off the critical path: the next step's noise.  The Philox step index is the host's
+        // count of enqueued steps, which the device counter equals when that step runs.
+        LaunchCtx side = h->ctx;
+        side.stream = h->stream2;
+        CK(cudaStreamWaitEvent(h->stream2, h->ev_chain_done, 0));
+        CK(launch_sample(side, h->d_eps_alt, h->d_ctl, true, h->steps_enqueued + 1));
+        CK(cudaEventRecord(h->ev_sampled, h->stream2));
+        std::swap(h->d_eps, h->d_eps_alt);
+        std::swap(h->tmap, h->tmap_alt);
+        std::swap(h->tmap_ro, h->tmap_ro_alt);
+        h->presampled = true;
+        h->total_launches += kernels_per_step(h, true);
+        h->steps_enqueued += 1;
+        h->pending = true;
+        return MPPI_OK;
+    }
+    // a step of any other kind advances the step counter: noise drawn ahead is void
+    // (the plain chain draws the same values again)
+    if ((rc = quiesce_side(h)) != MPPI_OK) return rc;
+    h->presampled = false;
     if (h->profiling || (h->p.flags & MPPI_FLAG_NO_GRAPH)) {
         rc = enqueue_chain(h, sample, h->profiling ? h->ev : nullptr);
         if (rc) return rc;
@@ -870,7 +985,7 @@ int mppi_get_info(mppi_handle *h, float *x, float *u, float *e, float *cost, flo
     if (e) {
         const size_t n = (size_t)c.k_local * h->R;
         CKS(cudaMalloc(&scratch, sizeof(float) * n));
-        CKS(launch_to_reference(c, h->d_eps, scratch));
+        CKS(launch_to_reference(c, last_eps(h), scratch));
         CKS(cudaMemcpyAsync(e, scratch, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
         CKS(cudaStreamSynchronize(h->stream));
         release();
@@ -878,7 +993,7 @@ int mppi_get_info(mppi_handle *h, float *x, float *u, float *e, float *cost, flo
     if (x) {
         const size_t n = (size_t)c.k_local * (h->p.horizon + 1) * h->S;
         CKS(cudaMalloc(&scratch, sizeof(float) * n));
-        CKS(launch_trajectories(c, h->d_eps, h->d_Uprev, h->d_prob, scratch));
+        CKS(launch_trajectories(c, last_eps(h), h->d_Uprev, h->d_prob, scratch));
         CKS(cudaMemcpyAsync(x, scratch, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
         CKS(cudaStreamSynchronize(h->stream));
         release();
@@ -913,6 +1028,7 @@ int mppi_set_noise(mppi_handle *h, const float *e)
     if (!e) return fail(MPPI_ERR_INVALID, "null argument");
     const LaunchCtx &c = h->ctx;
     const size_t n = (size_t)c.k_local * h->R;
+    if ((rc = quiesce_side(h)) != MPPI_OK) return rc;   // d_eps may be receiving noise drawn ahead
     float *scratch = nullptr;
     CK(cudaMalloc(&scratch, sizeof(float) * n));
     cudaError_t err = cudaMemcpyAsync(scratch, e, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream);
@@ -933,6 +1049,9 @@ int mppi_sample_only(mppi_handle *h, uint64_t step)
     }
     int rc = check_handle(h);
     if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    if ((rc = quiesce_side(h)) != MPPI_OK) return rc;
+    h->presampled = false;                               // d_eps is overwritten
     CK(launch_sample(h->ctx, h->d_eps, h->d_ctl, true, step));
     CK(cudaStreamSynchronize(h->stream));
     h->total_launches += 1;

@@ -57,6 +57,19 @@ def test_k_sharded_controller(comm):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("comm", ["nccl", "p2p"])
+def test_k_sharded_pipelined_sampling(comm):
+    """K-shards with MPPI_FLAG_PIPELINED_SAMPLING (512): every rank draws its shard of the next
+    step's noise behind the chain; three steps against the single-shard oracle."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    r = _launch(comm, min(n, 4), 29551 + (comm == "p2p"), "512")
+    assert r.returncode == 0 and comm.upper() + "_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.gpu
 def test_single_process_device_group(oracle):
     """mppi_create_multi: ONE process (the reference's process model, src/main.cu) drives
     several GPUs; K is sharded, the shards exchange through peer memory; the caller sees one

@@ -175,7 +175,8 @@ def test_auto_chain_picks_by_shard_size(M):
     from mppi_gpu_b200 import capi
     T, A = 10, 2
     cfg = REF_CFG[A]
-    want = {50000: 0, 150000: capi.FLAG_FUSED_SAMPLING, 450000: capi.FLAG_STEP_KERNEL}
+    want = {50000: capi.FLAG_PIPELINED_SAMPLING, 150000: capi.FLAG_FUSED_SAMPLING,
+            450000: capi.FLAG_STEP_KERNEL}
     for K, chain in want.items():
         ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=4, flags=capi.FLAG_AUTO_CHAIN)
         assert ctl.flags() == chain, (K, ctl.flags())
