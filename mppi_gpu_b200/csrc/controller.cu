@@ -87,8 +87,9 @@ struct mppi_handle {
     cudaEvent_t ev_sampled = nullptr;      // stream2: the noise drawn ahead is complete
     cudaEvent_t ev_chain_done = nullptr;   // stream: the last chain has finished reading its buffer
     cudaGraphExec_t graph_pipe[2] = {nullptr, nullptr};
-    bool presampled = false;   // d_eps holds (or is receiving) the noise of the next step,
-                               // d_eps_alt the noise the last step consumed
+    bool presampled = false;   // d_eps holds (or is receiving) the noise of the next step
+    float *eps_last = nullptr; // the noise the last step consumed (get_inf tap); == d_eps outside
+                               // the pipeline
     NcclComm comm;
     unsigned long long *d_mailbox = nullptr;              // MPPI_COMM_P2P: this rank's mailbox
     unsigned long long *peer_mb[kMaxWorld] = {};          // every rank's mailbox mapped here
@@ -127,7 +128,7 @@ bool pipelined(const mppi_handle *h, bool sample)
     return sample && h->d_eps_alt != nullptr && !h->profiling && !(h->p.flags & MPPI_FLAG_NO_GRAPH);
 }
 // the noise the last finished step consumed (get_inf tap)
-float *last_eps(const mppi_handle *h) { return h->presampled ? h->d_eps_alt : h->d_eps; }
+float *last_eps(const mppi_handle *h) { return h->eps_last ? h->eps_last : h->d_eps; }
 
 int encode_tmap(mppi_handle *h, CUtensorMap *out, int box_cols, int box_rows, float *base = nullptr)
 {
@@ -261,10 +262,20 @@ int build_pipe_graph(mppi_handle *h, int which)
     return MPPI_OK;
 }
 
-// noise drawn ahead may still be landing in d_eps: wait before anything else touches it
-int quiesce_side(mppi_handle *h)
+// Leave the pipeline before anything but a pipelined step touches eps: noise drawn ahead may
+// still be landing in d_eps (wait for it, then it is void -- whoever draws for that step next
+// gets the same values), and the plain graphs were captured on base buffer 0, so d_eps goes
+// back to it.  eps_last keeps pointing at the noise the last step consumed.
+int leave_pipeline(mppi_handle *h)
 {
-    if (h->stream2 && h->presampled) CK(cudaStreamSynchronize(h->stream2));
+    if (!h->stream2) return MPPI_OK;
+    if (h->presampled) CK(cudaStreamSynchronize(h->stream2));
+    h->presampled = false;
+    if (h->d_eps != h->eps_base[0]) {
+        std::swap(h->d_eps, h->d_eps_alt);
+        std::swap(h->tmap, h->tmap_alt);
+        std::swap(h->tmap_ro, h->tmap_ro_alt);
+    }
     return MPPI_OK;
 }
 
@@ -803,6 +814,7 @@ int mppi_step_enqueue(mppi_handle *h)
         CK(cudaStreamWaitEvent(h->stream2, h->ev_chain_done, 0));
         CK(launch_sample(side, h->d_eps_alt, h->d_ctl, true, h->steps_enqueued + 1));
         CK(cudaEventRecord(h->ev_sampled, h->stream2));
+        h->eps_last = h->d_eps;
         std::swap(h->d_eps, h->d_eps_alt);
         std::swap(h->tmap, h->tmap_alt);
         std::swap(h->tmap_ro, h->tmap_ro_alt);
@@ -814,8 +826,8 @@ int mppi_step_enqueue(mppi_handle *h)
     }
     // a step of any other kind advances the step counter: noise drawn ahead is void
     // (the plain chain draws the same values again)
-    if ((rc = quiesce_side(h)) != MPPI_OK) return rc;
-    h->presampled = false;
+    if ((rc = leave_pipeline(h)) != MPPI_OK) return rc;
+    h->eps_last = h->d_eps;
     if (h->profiling || (h->p.flags & MPPI_FLAG_NO_GRAPH)) {
         rc = enqueue_chain(h, sample, h->profiling ? h->ev : nullptr);
         if (rc) return rc;
@@ -1028,7 +1040,8 @@ int mppi_set_noise(mppi_handle *h, const float *e)
     if (!e) return fail(MPPI_ERR_INVALID, "null argument");
     const LaunchCtx &c = h->ctx;
     const size_t n = (size_t)c.k_local * h->R;
-    if ((rc = quiesce_side(h)) != MPPI_OK) return rc;   // d_eps may be receiving noise drawn ahead
+    if ((rc = leave_pipeline(h)) != MPPI_OK) return rc;   // d_eps may be receiving noise drawn ahead
+    h->eps_last = h->d_eps;
     float *scratch = nullptr;
     CK(cudaMalloc(&scratch, sizeof(float) * n));
     cudaError_t err = cudaMemcpyAsync(scratch, e, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream);
@@ -1050,8 +1063,8 @@ int mppi_sample_only(mppi_handle *h, uint64_t step)
     int rc = check_handle(h);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    if ((rc = quiesce_side(h)) != MPPI_OK) return rc;
-    h->presampled = false;                               // d_eps is overwritten
+    if ((rc = leave_pipeline(h)) != MPPI_OK) return rc;
+    h->eps_last = h->d_eps;                              // what get_inf returns next
     CK(launch_sample(h->ctx, h->d_eps, h->d_ctl, true, step));
     CK(cudaStreamSynchronize(h->stream));
     h->total_launches += 1;

@@ -99,13 +99,25 @@ def test_pipelined_survives_mode_switches(M):
         assert np.array_equal(bits(na0), bits(na1)), tag
         _same_state(plain, pipe)
 
+    # leave the pipeline after an odd and after an even number of pipelined steps: the plain
+    # graphs are bound to one eps buffer, the pipeline alternates between two
     check("sampled 0")
-    check("sampled 1")
     both(lambda c: c.set_noise(eps))                # switches to injected mode
-    check("injected")
+    check("injected after 1 pipelined step")
     both(lambda c: c.set_noise_mode(False))
     check("sampled after injected")                 # must re-prime: the counter moved on
     check("sampled, pipelined again")
+    both(lambda c: c.set_noise(eps[::-1].copy()))
+    check("injected after 2 pipelined steps")
+    check("injected again")
+    both(lambda c: c.set_noise_mode(False))
+    check("sampled 1")
+    check("sampled 2")
+    check("sampled 3")
+    both(lambda c: c.set_noise(eps))
+    check("injected after 3 pipelined steps")
+    both(lambda c: c.set_noise_mode(False))
+    check("sampled 4")
     both(lambda c: c.set_profiling(True))
     check("profiled step (plain chain)")
     both(lambda c: c.set_profiling(False))
