@@ -262,6 +262,13 @@ int mppi_comm_p2p_connect(mppi_handle *h, const uint8_t *handles);
 const char *mppi_last_error(void);
 int mppi_abi_version(void);
 
+/* Environment variables read at mppi_create -- kernel-variant overrides for tests and
+ * tuning, never needed in production (every variant computes the same bits):
+ *   MPPI_ROLLOUT_TMA=0|1      force the register-pipelined / the TMA-staged rollout kernel
+ *   MPPI_ROLLOUT_TMA_W=64|128|256   slab width of the TMA-staged rollout
+ *   MPPI_ROLLOUT_SPT=1|2|4    samples per thread of the register-pipelined rollout
+ *   MPPI_STEP_STAGES=4|8      TMA ring depth of the one-kernel step                      */
+
 #ifdef __cplusplus
 }
 #endif
