@@ -11,8 +11,9 @@ namespace mppi {
 // next_act points into PINNED HOST memory mapped into the device (zero copy): the kernel stores
 // the A floats of the next action and the exchange-error flag straight into the caller's
 // process, then publishes the step counter at next_act + kNextSeqOffset with a system-scope
-// release.  The host spins on that word instead of waiting for a D2H copy node and a stream
-// synchronisation (mppi_step_wait) -- several microseconds of a closed-loop control step.
+// release -- as soon as the new U[0] is known, before the shift.  The host spins on that word
+// instead of waiting for a D2H copy node and a stream synchronisation (mppi_step_wait) --
+// several microseconds of a closed-loop control step.
 constexpr int kNextSeqOffset = 2 * kMaxAct;     // in floats; 8-byte aligned
 constexpr int kNextFloats = 2 * kMaxAct + 2;
 __device__ __forceinline__ void finalize_body(long long *acc, float *__restrict__ U,
@@ -38,6 +39,18 @@ __device__ __forceinline__ void finalize_body(long long *acc, float *__restrict_
         s_u[i] = un;
     }
     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nt) : "memory");
+    // Publish first: the action is all the caller is waiting for.  One thread stores the A
+    // floats and the exchange-error flag and then the step counter with a system-scope release,
+    // which orders its own earlier stores before it -- one round trip to host memory.  The
+    // shift and the re-arming below finish while the host is already on its way; whatever it
+    // does to this handle next is ordered behind this kernel by the stream.
+    unsigned long long step = 0;
+    if (threadIdx.x == 0) {
+        step = ctl->step + 1;
+        for (int a = 0; a < A; ++a) next_act[a] = s_u[a];
+        next_act[kMaxAct] = ctl->comm_error ? 1.0f : 0.0f;               // read with next_act
+        st_release_sys_u64(reinterpret_cast<unsigned long long *>(next_act + kNextSeqOffset), step);
+    }
     for (int i = threadIdx.x; i < R; i += nt) {
         float v;
         if (i < R - A)                              v = s_u[i + A];
@@ -46,21 +59,13 @@ __device__ __forceinline__ void finalize_body(long long *acc, float *__restrict_
         U[i] = v;
         acc[i] = 0;
     }
-    if (threadIdx.x < 32) {
-        if (threadIdx.x < A) next_act[threadIdx.x] = s_u[threadIdx.x];
-        if (threadIdx.x == A) next_act[kMaxAct] = ctl->comm_error ? 1.0f : 0.0f;   // read with next_act
-        __threadfence_system();
-        __syncwarp();
-    }
     if (threadIdx.x == 0) {
         acc[R] = 0;
         ctl->eta = eta;
         ctl->last_key = ctl->min_key;
         ctl->min_key = kMinKeyInit;
-        const unsigned long long step = ctl->step + 1;
         ctl->step = step;
         ctl->done = 0;
-        st_release_sys_u64(reinterpret_cast<unsigned long long *>(next_act + kNextSeqOffset), step);
     }
 }
 
