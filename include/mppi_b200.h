@@ -194,7 +194,10 @@ int mppi_set_state(mppi_handle *h, const float *x);
 /* == get_act(next_act) (src/point_mass.cu:129-203): one control step; writes the
  * A floats of U[0,:] *before* the shift; U is left already shifted. Blocking: the
  * finalizing kernel stores the action and the step counter into pinned host memory
- * mapped into the device, and the call returns as soon as that counter shows up. */
+ * mapped into the device as soon as the new U[0,:] is known, and the call returns as
+ * soon as that counter shows up; the shift itself (and, with
+ * MPPI_FLAG_PIPELINED_SAMPLING, the next step's noise) completes behind it on the
+ * handle's streams, which every other call on the handle is ordered after. */
 int mppi_step(mppi_handle *h, float *next_act);
 
 /* The two halves of mppi_step for callers that overlap host work: enqueue the
