@@ -22,7 +22,16 @@ Printed JSON line (rank 0):
                three-kernel) with their per-kernel times and HBM fractions
   cpu_baseline the reference's own model/cost code (oracle/_ref) + oracle port of the
                reductions, 1 core, on a bounded sample of the workload
-`--impl reference` times that CPU path with all host threads instead.
+  parity_check one small K-sharded step of the SAME chain on the SAME ranks before the timing:
+               noise and costs gathered from all ranks, single-shard oracle on rank 0 (checker
+               only): S bit exact, beta / argmin exact, U within 1e-5, U bit-identical on every
+               rank; a failure exits non-zero
+  collectives_ms (N > 1) the NVLink exchange of the timed chain (push / wait-for-slowest /
+               merge, %globaltimer stamps) AND, from a second controller on the same shards, the
+               two NCCL all-reduces (min, sum) of the MPPI_COMM_NCCL chain
+  configs      (N = 1) BASELINE.json configs[1] and [4] through the same API with host buffers:
+               point_mass2d K=1e4 (ms_per_step, p50, p99) and the 1000-step closed loop at K=1e5
+`--impl reference` times that CPU path with all host threads instead, on the full workload.
 """
 import argparse
 import json
@@ -54,6 +63,16 @@ UNIT = "rollout-steps/s"
 def workload_desc(name, K, T, A):
     return (f"{name}: K={K} global samples, T={T}, A={A}, S={2 * A}, dt=0.1, x0=0, U0=0, "
             f"lambda=1, sigma=0.025 (reference-compat preset), Philox seed 0")
+
+
+def config_dict(name, K, T, A):
+    """The `config` object of the JSON line -- identical for both arms (--impl ours|reference),
+    so that the driver compares like with like; everything arm-specific goes to `details`."""
+    eps_mb = 4.0 * K * T * A / 1e6
+    return {"workload": workload_desc(name, K, T, A),
+            "l2": ("inputs larger than L2: eps is %.0f MB per pass over all shards vs 126 MB of L2, "
+                   "no flush between steps" % eps_mb) if eps_mb > 200 else
+                  ("working set fits L2 (%.0f MB of eps): latency-bound config, no flush" % eps_mb)}
 
 
 # --------------------------------------------------------------------------------- clocks
@@ -135,19 +154,28 @@ def cpu_reference_step(po, K, T, A, dt, goal, w, x0, U, eps, nthreads):
 
 
 def cpu_sample_inputs(K, T, A):
-    rs = np.random.RandomState(0)
-    eps = (0.025 * rs.standard_normal((K, T, A))).astype(np.float32)
+    eps = np.random.default_rng(0).standard_normal((K, T, A), dtype=np.float32)
+    eps *= np.float32(0.025)
     return np.zeros(2 * A, np.float32), np.zeros((T, A), np.float32), eps
 
 
 def run_reference(args, name, K, T, A, dt, goal, w):
+    """The reference's own CPU implementation of the path on the box's host cores, all threads,
+    on the FULL workload (same K, T, A as the product arm): at K=1e6 a step is ~1 s on 32
+    threads.  Only if a single step would take longer than ~20 s (estimated from a 2 % probe)
+    is K cut, and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import pyoracle as po
     po.lib()
     nthreads = os.cpu_count() or 1
-    Ks = min(K, 100000)
+    probe = max(1000, K // 50)
+    x0, U, eps = cpu_sample_inputs(min(K, probe), T, A)
+    cpu_reference_step(po, len(eps), T, A, dt, goal, w, x0, U, eps, nthreads)
+    t_probe = cpu_reference_step(po, len(eps), T, A, dt, goal, w, x0, U, eps, nthreads)
+    est = t_probe * K / len(eps)
+    Ks = K if est <= 20.0 else max(probe, int(K * 20.0 / est))
     x0, U, eps = cpu_sample_inputs(Ks, T, A)
     for _ in range(args.warmup):
         cpu_reference_step(po, Ks, T, A, dt, goal, w, x0, U, eps, nthreads)
@@ -156,7 +184,8 @@ def run_reference(args, name, K, T, A, dt, goal, w):
     sec = sum(times) / len(times)
     val = Ks * T / sec
     kind = "reference" if po.ref_available() else "port"
-    sample = (f"{Ks} of {K} samples per step (same T, A); rollout+cost = "
+    sample = (("the full workload, " if Ks == K else f"{Ks} of {K} samples per step (same T, A), ")
+              + "rollout+cost = "
               + ("the reference's point_mass_gpu.cu+cost.cu compiled for the host (oracle/_ref), "
                  "OpenMP over samples" if kind == "reference" else "oracle port, OpenMP over samples")
               + "; beta/exp/eta/weights/shift = oracle port (serial), update_act_cpu = oracle port "
@@ -165,12 +194,155 @@ def run_reference(args, name, K, T, A, dt, goal, w):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": workload_desc(name, K, T, A)},
+        "data": "synthetic", "config": config_dict(name, K, T, A),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": kind,
                          "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# --------------------------------------------------------------------------------- parity
+PARITY_SHAPE = (20003, 40, 3, 5.0)      # K, T, A, lambda  (tests/dist_worker.py: gpu_mode)
+
+
+def parity_check(m, capi, dist, torch, rank, world, local_rank, flags, comm):
+    """One small step of the chain that is about to be timed, on the same ranks: the sampled
+    noise and the costs of every shard are gathered, rank 0 runs the single-shard oracle on
+    them (the checker; reference semantics: PointMassModel::get_act, src/point_mass.cu:129-203)
+    and compares.  Bars: S bit exact, beta and argmin exact, eta / U / next action within 1e-5,
+    replicated U bit-identical on every rank.  Returns the dict for the JSON line."""
+    K, T, A, lam = PARITY_SHAPE
+    goal, w = [1, .5, .75, 0, 0, 0], [1, 1, 1, 5, 5, 5]
+    rs = np.random.RandomState(3)
+    U = (0.1 * rs.standard_normal((T, A))).astype(np.float32)
+    x0 = (0.05 * rs.standard_normal(2 * A)).astype(np.float32)
+    if world > 1:
+        from mppi_gpu_b200.torch_dist import sharded_controller
+        ctl = sharded_controller(K, T, 0.1, 2 * A, A, comm=comm, device=local_rank, lam=lam,
+                                 seed=11, flags=flags)
+    else:
+        ctl = m.PointMassModel(K, T, 0.1, 2 * A, A, lam=lam, seed=11, flags=flags, device=local_rank)
+    ctl.memcpy_set_data(x0, U, goal, w)
+    k0, k1 = capi.shard_range(K, rank, world)
+    res = {"n": world, "shape": f"K={K},T={T},A={A},lambda={lam}", "flags": ctl.flags(), "steps": 2}
+    ok, why = True, ""
+    for step in range(2):
+        pre = ctl.get_u()
+        na = ctl.get_act()
+        inf = ctl.get_inf()
+        info = ctl.step_info()
+        if world > 1:
+            sizes = [capi.shard_range(K, r, world)[1] - capi.shard_range(K, r, world)[0]
+                     for r in range(world)]
+            kmax = max(sizes)
+            e_pad = torch.zeros(kmax * T * A, dtype=torch.float32, device="cuda")
+            c_pad = torch.zeros(kmax, dtype=torch.float32, device="cuda")
+            e_pad[: (k1 - k0) * T * A] = torch.from_numpy(inf["e"].ravel()).cuda()
+            c_pad[: k1 - k0] = torch.from_numpy(inf["cost"]).cuda()
+            e_all = [torch.zeros_like(e_pad) for _ in range(world)]
+            c_all = [torch.zeros_like(c_pad) for _ in range(world)]
+            dist.all_gather(e_all, e_pad)
+            dist.all_gather(c_all, c_pad)
+            eps = torch.cat([e[: n * T * A] for e, n in zip(e_all, sizes)]).cpu().numpy().reshape(K, T, A)
+            cost = torch.cat([c[:n] for c, n in zip(c_all, sizes)]).cpu().numpy()
+            u_all = [torch.zeros(T * A + A, dtype=torch.float32, device="cuda") for _ in range(world)]
+            mine = torch.from_numpy(np.concatenate([inf["u"].ravel(), na])).cuda()
+            dist.all_gather(u_all, mine)
+            same = all(torch.equal(u.view(torch.int32), u_all[0].view(torch.int32)) for u in u_all[1:])
+        else:
+            eps, cost, same = inf["e"], inf["cost"], True
+        if rank == 0:
+            from oracle import pyoracle as po                       # the checker, never the product
+            po.lib()
+            p = po.make_problem(K, T, A, 0.1, goal, w, lam=lam, arith=po.ARITH_FMA)
+            ref = po.step(p, x0, pre, eps, nthreads=min(8, os.cpu_count() or 1))
+            checks = {
+                "S_bit_exact": bool(np.array_equal(cost.view(np.uint32), ref["S"].view(np.uint32))),
+                "beta_exact": bool(np.float32(inf["beta"]).view(np.uint32) == np.float32(ref["beta"]).view(np.uint32)),
+                "argmin_exact": bool(info["argmin"] == ref["argmin"]),
+                "eta_1e-5": bool(abs(float(inf["nabla"]) - float(ref["eta"])) <= 1e-5 * float(ref["eta"])),
+                "U_1e-5": bool(np.allclose(inf["u"], ref["U"], rtol=1e-5, atol=1e-6)),
+                "next_act_1e-5": bool(np.allclose(na, ref["next_act"], rtol=1e-5, atol=1e-6)),
+                "U_bit_identical_across_ranks": bool(same),
+            }
+            res["max_abs_dU"] = float(np.abs(inf["u"] - ref["U"]).max())
+            bad = [k for k, v in checks.items() if not v]
+            if bad:
+                ok, why = False, f"step {step}: " + ",".join(bad)
+            res["checks"] = checks
+    ctl.close()
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    if dist is not None:
+        dist.broadcast(flag, 0)
+    res["ok"] = bool(flag.item())
+    if why:
+        res["failed"] = why
+    return res
+
+
+# --------------------------------------------------------------------------------- extra configs
+def closed_loop_config(m, capi, local_rank, nsteps=1000):
+    """BASELINE.json configs[4]: receding-horizon point_mass2d, K=1e5, T=200, one CUDA graph per
+    control step, the reference's loop (src/main.cu:326-371: get_act -> plant -> set_x) with the
+    ideal double-integrator plant (the controller's own model) on the host."""
+    K, T, A, dt, goal, w = WORKLOADS["point_mass2d_K1e5_T200"]
+    ctl = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=capi.FLAG_AUTO_CHAIN, device=local_rank)
+    x = np.zeros(2 * A, np.float32)
+    ctl.memcpy_set_data(x, np.zeros((T, A), np.float32), goal, w)
+    act = np.zeros(A, np.float32)
+    for _ in range(20):
+        ctl.get_act(act)
+    ctl.memcpy_set_data(x, np.zeros((T, A), np.float32), goal, w)
+    lat, plant = [], []
+    for _ in range(nsteps):
+        t0 = time.perf_counter()
+        ctl.get_act(act)
+        t1 = time.perf_counter()
+        a = np.clip(act, -1.0, 1.0)
+        x[:A] += dt * x[A:] + 0.5 * dt * dt * a
+        x[A:] += dt * a
+        ctl.set_x(x)
+        t2 = time.perf_counter()
+        lat.append(t1 - t0)
+        plant.append(t2 - t1)
+    flags = ctl.flags()
+    ctl.close()
+    lat = sorted(1e3 * v for v in lat)
+    return {"workload": "point_mass2d, K=1e5, T=200, 1000 closed-loop control steps, graph per step",
+            "p50_ms": lat[len(lat) // 2], "p99_ms": lat[int(0.99 * len(lat))], "max_ms": lat[-1],
+            "plant_us": 1e6 * statistics.median(plant), "flags": flags,
+            "final_state": [float(v) for v in x],
+            "rollout_steps_per_s_p50": K * T / (lat[len(lat) // 2] * 1e-3)}
+
+
+def small_config(m, capi, local_rank, name, nsteps=200):
+    """BASELINE.json configs[1] (and [0]'s shape on the GPU): device time per step and the
+    latency of set_x + get_act with host buffers."""
+    K, T, A, dt, goal, w = WORKLOADS[name]
+    ctl = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=capi.FLAG_AUTO_CHAIN, device=local_rank)
+    x = np.zeros(2 * A, np.float32)
+    ctl.memcpy_set_data(x, np.zeros((T, A), np.float32), goal, w)
+    act = np.zeros(A, np.float32)
+    for _ in range(20):
+        ctl.get_act(act)
+    ctl.timer_start()
+    for _ in range(nsteps):
+        ctl.step_enqueue()
+    ms = ctl.timer_stop() / nsteps
+    ctl.step_wait()
+    lat = []
+    for _ in range(nsteps):
+        t0 = time.perf_counter()
+        ctl.set_x(x)
+        ctl.get_act(act)
+        lat.append(time.perf_counter() - t0)
+        x[:A] = 1e-3 * act
+    flags = ctl.flags()
+    ctl.close()
+    lat = sorted(1e3 * v for v in lat)
+    return {"ms_per_step": ms, "rollout_steps_per_s": K * T / (ms * 1e-3), "p50_ms": lat[len(lat) // 2],
+            "p99_ms": lat[int(0.99 * len(lat))], "flags": flags}
 
 
 # --------------------------------------------------------------------------------- ours
@@ -203,13 +375,8 @@ def run_ours(args, name, K, T, A, dt, goal, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # chain selection: with >= 4e5 samples per GPU the sampling is fused into the rollout (one
-    # pass writes eps and integrates; identical eps values) -- on a single shard as the
-    # one-kernel step, where the weighted average of finished tiles overlaps the rollout of
-    # the next ones; below that the step is latency-bound and the unfused chain with the TMA
-    # rollout wins.
-    k_loc = capi.shard_range(K, rank, world)
-    k_loc = k_loc[1] - k_loc[0]
+    # chain selection: MPPI_FLAG_AUTO_CHAIN lets the library choose from the shard's shape; the
+    # choice is read back and reported (details.flags / details.chain)
     flags = args.flags if args.flags >= 0 else capi.FLAG_AUTO_CHAIN
     if world > 1:
         from mppi_gpu_b200.torch_dist import sharded_controller
@@ -220,6 +387,18 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     flags = ctl.flags()                       # MPPI_FLAG_AUTO_CHAIN resolved by the library
     x0 = np.zeros(2 * A, np.float32)
     ctl.memcpy_set_data(x0, np.zeros((T, A), np.float32), goal, w)
+
+    # ---- parity first: the chain about to be timed, on these ranks, against the oracle
+    parity = None
+    if not args.no_parity_check:
+        parity = parity_check(m, capi, dist, torch, rank, world, local_rank, flags, args.comm)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world,
+                                  "parity_check": parity, "error": "parity check failed"}))
+            if dist is not None:
+                dist.destroy_process_group()
+            raise SystemExit(3)
 
     # ---- warm-up (also instantiates the CUDA graph)
     for _ in range(max(args.warmup, 3)):
@@ -248,6 +427,7 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     x_host = np.zeros(2 * A, np.float32)
     act_host = np.zeros(A, np.float32)
     lat = []
+    xt = {"push_us": [], "wait_slowest_us": [], "merge_us": []}
     barrier()
     t_begin = time.perf_counter()
     for i in range(args.steps):
@@ -261,6 +441,12 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     e2e_sec = max_over_ranks(e2e_sec)
     e2e_val = K * T / e2e_sec
     lat_ms = sorted(1e3 * x for x in lat)
+    if world > 1 and args.comm == "p2p":
+        # phases of the in-kernel NVLink exchange (%globaltimer stamps of the last step)
+        for _ in range(min(args.steps, 20)):
+            ctl.get_act(act_host)
+            for k, v in ctl.exchange_times().items():
+                xt[k].append(v)
 
     # ---- region 3: the same chain with CUDA events between the kernels
     ctl.set_profiling(True)
@@ -272,88 +458,128 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     clk = clocks.stop() if rank == 0 else None
 
     k_local = ctl.k_local
-    one_kernel = bool(flags & capi.FLAG_STEP_KERNEL) and launches == args.steps * (1 if world == 1 else 2)
+    tile_kernel = bool(flags & capi.FLAG_TILE_KERNEL) and launches == args.steps
+    one_kernel = tile_kernel or (bool(flags & capi.FLAG_STEP_KERNEL) and launches == args.steps)
     avg_ms = max_over_ranks(kernels["average"])
+    units = float(k_local) * T                      # rollout-steps one launch of this shard processes
     if one_kernel:
-        # eps written once and read back once, S written and read once.  The step IS this one
-        # kernel, so its average launch duration is taken from region 1 (K launches back to
-        # back between two CUDA events; includes the 20-byte D2H node) rather than from region
-        # 3, whose per-launch event pairs add the launch gap.
-        alg_bytes = 8.0 * k_local * T * A + 8.0 * k_local
-        if world == 1:
-            avg_ms = ms_step
-    else:
-        alg_bytes = 4.0 * k_local * T * A + 4.0 * k_local
+        # The step IS this one kernel, so its average launch duration is taken from region 1
+        # (K launches back to back between two CUDA events) rather than from region 3, whose
+        # per-launch event pairs add the launch gap.
+        avg_ms = ms_step
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    # Algorithmic bytes.  SURVEY.md 8(d): 12*A bytes per rollout-step (+16/T) -- eps written by the
+    # sampler, read by the rollout, read by the average.  A chain that hands eps from the sampler
+    # to the rollout in registers moves 8*A (+8/T): round 1's accounting, kept as `frac_fused_design`.
+    # The dominant kernel of the unfused chains (average_kernel) is accounted with its own 4*A.
+    survey_bytes = 12.0 * A * units + 16.0 * k_local
+    fused_bytes = 8.0 * A * units + 8.0 * k_local
+    if one_kernel:
+        alg_bytes = survey_bytes
+    else:
+        alg_bytes = 4.0 * A * units + 4.0 * k_local
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
-    ncu_traffic = None
+    traffic_file = ("tile_traffic.json" if tile_kernel else "step_traffic.json" if one_kernel
+                    else "average_traffic.json")
+    ncu_traffic, traffic_src = None, None
     try:
-        ncu_traffic = json.load(open(os.path.join(
-            ROOT, "profiles", "step_traffic.json" if one_kernel else "average_traffic.json"))).get(
-            "dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))
+        if world == 1 and name == DEFAULT_WORKLOAD:
+            ncu_traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = {k: tj.get(k) for k in ("source", "commit", "kernel", "captured") if k in tj}
+            traffic_src["file"] = "profiles/" + traffic_file
     except Exception:
         pass
-    roofline = {"kernel": ("step_kernel (parts 1-5 in one persistent kernel: eps written by the rollout "
-                           "warps, read back by the TMA-fed average warps)" if one_kernel else
-                           "average_kernel (part 4: sum_k w_k eps_k[t,a])"), "bound": "hbm",
+    if tile_kernel:
+        kname = ("tile_kernel (parts 1-5 in one persistent kernel; eps drawn into shared memory, "
+                 "integrated and averaged there -- it never reaches HBM)")
+        note = ("achieved = SURVEY 8(d) algorithmic bytes (12*A per rollout-step) / launch time: the "
+                "kernel beats the HBM roofline of the path (frac > 1) because it does not move those "
+                "bytes -- measured DRAM traffic in `traffic`; what bounds it is instruction issue "
+                "(Philox + Box-Muller), see `issue`")
+    elif one_kernel:
+        kname = ("step_kernel (parts 1-5 in one persistent kernel: eps written by the rollout "
+                 "warps, read back by the TMA-fed average warps)")
+        note = "frac follows SURVEY 8(d) (12*A); the kernel itself moves 8*A: frac_fused_design"
+    else:
+        kname, note = "average_kernel (part 4: sum_k w_k eps_k[t,a])", "4*A bytes per rollout-step: this pass only"
+    roofline = {"kernel": kname, "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
-                "traffic": ncu_traffic if world == 1 and name == DEFAULT_WORKLOAD else None}
+                "traffic": ncu_traffic, "traffic_source": traffic_src, "note": note}
+    if one_kernel:
+        roofline["frac_survey_bytes"] = survey_bytes / (avg_ms * 1e-3) / 1e9 / peak
+        roofline["frac_fused_design"] = fused_bytes / (avg_ms * 1e-3) / 1e9 / peak
+        roofline["survey_bytes_per_launch"] = survey_bytes
+        roofline["fused_design_bytes_per_launch"] = fused_bytes
+    if tile_kernel:
+        try:
+            roofline["issue"] = json.load(open(os.path.join(ROOT, "profiles", "tile_issue.json")))
+        except Exception:
+            roofline["issue"] = None
     eps_bytes = 4.0 * k_local * T * A
     per_kernel = {}
-    for kname, ms in kernels.items():
+    for kname_, ms in kernels.items():
         d = {"ms": ms}
-        if kname in ("sample", "rollout"):
+        if kname_ in ("sample", "rollout"):
             d["hbm_gbs"] = eps_bytes / (ms * 1e-3) / 1e9
             d["hbm_frac"] = d["hbm_gbs"] / peak
-        per_kernel[kname] = d
+        per_kernel[kname_] = d
 
+    chain = ("one kernel, eps on chip: generator warps -> shared-memory tile -> integrator warp -> "
+             "averaging threads -> merge+finalize" + (" + NVLink exchange in the last CTA" if world > 1 else "")
+             if tile_kernel else
+             "one kernel: sample+rollout warps || weights+average warps -> merge+finalize"
+             + (" + NVLink exchange in the last CTA" if world > 1 else "")
+             if one_kernel else
+             "sample+rollout(fused) -> weights -> average -> finalize"
+             if flags & capi.FLAG_FUSED_SAMPLING else
+             "rollout -> weights -> average -> finalize; the sampler of step n+1 runs "
+             "behind step n's chain on a second stream (pipelined sampling)"
+             if flags & capi.FLAG_PIPELINED_SAMPLING else
+             "sample -> rollout -> weights -> average -> finalize")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_desc(name, K, T, A), "k_local": k_local,
-                   "l2": "inputs larger than L2 (eps %.0f MB per GPU per pass vs 126 MB L2)"
-                         % (eps_bytes / 1e6) if eps_bytes > 200e6 else
-                         "working set fits L2 (%.0f MB eps): latency-bound config, no flush" % (eps_bytes / 1e6),
-                   "flags": flags, "graph": not (flags & capi.FLAG_NO_GRAPH),
-                   "chain": ("one kernel: sample+rollout warps || weights+average warps -> merge+finalize"
-                             if one_kernel else
-                             "sample+rollout(fused) -> weights -> average -> finalize"
-                             if flags & capi.FLAG_FUSED_SAMPLING else
-                             "rollout -> weights -> average -> finalize; the sampler of step n+1 runs "
-                             "behind step n's chain on a second stream (pipelined sampling)"
-                             if flags & capi.FLAG_PIPELINED_SAMPLING else
-                             "sample -> rollout -> weights -> average -> finalize"),
-                   "timing": "value: CUDA events on the controller stream around K graph launches; "
-                             "kernels/roofline: CUDA events between kernels in a second region of K steps"},
+        "config": config_dict(name, K, T, A),
+        "details": {"k_local": k_local, "flags": flags, "graph": not (flags & capi.FLAG_NO_GRAPH),
+                    "chain": chain,
+                    "timing": "value: CUDA events on the controller stream around K graph launches; "
+                              "kernels/roofline: CUDA events between kernels in a second region of K steps"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4 * 2 * A,
                 "d2h_bytes_per_step": 4 * A, "ms_per_step": e2e_sec * 1e3},
         "latency_ms": {"p50": lat_ms[len(lat_ms) // 2], "p99": lat_ms[min(len(lat_ms) - 1, int(0.99 * len(lat_ms)))],
                        "min": lat_ms[0], "max": lat_ms[-1]},
         "gpu_launches": launches,
+        "parity_check": parity,
         "roofline": roofline,
         "kernels": per_kernel,
         "clocks": clk,
     }
     if one_kernel:
-        per_kernel = {"step": {"ms": avg_ms, "hbm_gbs": achieved, "hbm_frac": achieved / peak,
-                               "ms_with_event_pairs": kernels["average"]}}
+        per_kernel = {("tile" if tile_kernel else "step"): {
+            "ms": avg_ms, "alg_gbs": achieved, "alg_frac": achieved / peak,
+            "ms_with_event_pairs": kernels["average"]}}
         out["kernels"] = per_kernel
-    if world == 1 and flags & (capi.FLAG_FUSED_SAMPLING | capi.FLAG_STEP_KERNEL):
-        # the kernel chains timed beside it on the same workload: fused (sample+rollout, average)
-        # and the canonical unfused one (sample, rollout, average)
+    if world == 1 and name == DEFAULT_WORKLOAD and not args.no_other_chains:
+        # the other chains timed beside it on the same workload: the HBM one-kernel step, the
+        # fused two-kernel chain and the canonical unfused one (sample, rollout, average)
         ctl.close()
         ctl = None
-        base = flags & ~(capi.FLAG_FUSED_SAMPLING | capi.FLAG_STEP_KERNEL)
+        base = flags & ~(capi.FLAG_FUSED_SAMPLING | capi.FLAG_STEP_KERNEL | capi.FLAG_TILE_KERNEL |
+                         capi.FLAG_PIPELINED_SAMPLING)
         others = {}
-        for cname, cflags in (("fused_2_kernels", base | capi.FLAG_FUSED_SAMPLING), ("unfused_3_kernels", base)):
+        for cname, cflags in (("tile_kernel_eps_on_chip", base | capi.FLAG_TILE_KERNEL),
+                              ("step_kernel_eps_via_hbm", base | capi.FLAG_STEP_KERNEL),
+                              ("fused_2_kernels", base | capi.FLAG_FUSED_SAMPLING),
+                              ("unfused_3_kernels", base)):
             if cflags == flags:
                 continue
             c2 = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=cflags, device=local_rank)
@@ -371,26 +597,74 @@ def run_ours(args, name, K, T, A, dt, goal, w):
             kt4 = {k: ms / n for k, (ms, n) in c2.kernel_times().items() if n}
             c2.set_profiling(False)
             c2.close()
+            one = bool(cflags & (capi.FLAG_STEP_KERNEL | capi.FLAG_TILE_KERNEL))
             others[cname] = {
                 "ms_per_step": ms4, "value": K * T / (ms4 * 1e-3),
+                "frac_survey_bytes": survey_bytes / (ms4 * 1e-3) / 1e9 / peak,
                 "kernels": {k: ({"ms": v, "hbm_gbs": eps_bytes / (v * 1e-3) / 1e9,
                                  "hbm_frac": eps_bytes / (v * 1e-3) / 1e9 / peak}
-                                if k in ("sample", "rollout", "average") else {"ms": v})
+                                if (k in ("sample", "rollout", "average") and not one) else {"ms": v})
                             for k, v in kt4.items()}}
         out["other_chains"] = others
     if world > 1:
+        med = lambda v: statistics.median(v) if v else None
+        coll = {"comm": args.comm}
         if args.comm == "p2p":
-            out["collectives_ms"] = {
-                "kind": "ONE exchange per step over NVLink peer mailboxes (direct P2P stores + flags): "
-                        "every shard averages relative to its own minimum, the exchange kernel rescales "
-                        "by exp(-(beta_r-beta)/lambda), sums in rank order and applies the U update",
-                "min_u64": None,
-                "merge_i64+finalize": kernels.get("comm_sum")}
+            coll["p2p"] = {
+                "kind": "ONE exchange per step over NVLink peer mailboxes (direct P2P stores + flags), "
+                        + ("inside the last CTA of the step's kernel" if one_kernel else
+                           "in a single-CTA kernel behind average_kernel")
+                        + ": every shard averages relative to its own minimum, the exchange rescales "
+                          "by exp(-(beta_r-beta)/lambda), sums in rank order and applies the U update",
+                "push_us": med(xt["push_us"]), "wait_slowest_us": med(xt["wait_slowest_us"]),
+                "merge_us": med(xt["merge_us"]),
+                "kernel_ms": kernels.get("comm_sum")}
         else:
-            out["collectives_ms"] = {
-                "kind": "ncclAllReduce(min) + ncclAllReduce(sum) inside the CUDA graph",
-                "min_u64": kernels.get("comm_min"), "sum_i64": kernels.get("comm_sum")}
-        out["config"]["comm"] = args.comm
+            coll["nccl"] = {"min_u64": kernels.get("comm_min"), "sum_i64": kernels.get("comm_sum")}
+        if args.comm == "p2p" and not args.no_nccl_leg:
+            # the two NCCL all-reduces of the MPPI_COMM_NCCL chain, measured on a second
+            # controller over the same shards (north_star: reported separately)
+            if ctl is not None:
+                ctl.close()
+                ctl = None
+            from mppi_gpu_b200.torch_dist import sharded_controller
+            cn = sharded_controller(K, T, dt, 2 * A, A, comm="nccl", device=local_rank, seed=0,
+                                    flags=capi.FLAG_FUSED_SAMPLING)
+            cn.memcpy_set_data(x0, np.zeros((T, A), np.float32), goal, w)
+            for _ in range(5):
+                cn.get_act()
+            barrier()
+            cn.timer_start()
+            for _ in range(args.steps):
+                cn.step_enqueue()
+            ms_n = cn.timer_stop() / args.steps
+            cn.step_wait()
+            barrier()
+            cn.set_profiling(True)
+            for _ in range(20):
+                cn.get_act()
+            ktn = {k: ms / n for k, (ms, n) in cn.kernel_times().items() if n}
+            cn.set_profiling(False)
+            cn.close()
+            coll["nccl"] = {
+                "kind": "ncclAllReduce(min, 1 x u64 packed key) + ncclAllReduce(sum, (T*A+1) x int64) "
+                        "captured in the CUDA graph of the fused two-kernel chain",
+                "min_u64": max_over_ranks(ktn.get("comm_min", 0.0)),
+                "sum_i64": max_over_ranks(ktn.get("comm_sum", 0.0)),
+                "ms_per_step": max_over_ranks(ms_n),
+                "value": K * T / (max_over_ranks(ms_n) * 1e-3)}
+        out["collectives_ms"] = coll
+        out["details"]["comm"] = args.comm
+
+    # ---- BASELINE.json configs[1] and [4] through the same API (N=1 only; < 2 s)
+    if rank == 0 and world == 1 and name == DEFAULT_WORKLOAD and not args.no_extra_configs:
+        if ctl is not None:
+            ctl.close()
+            ctl = None
+        out["configs"] = {
+            "point_mass1d_K1e4_T200": small_config(m, capi, local_rank, "point_mass1d_K1e4_T200"),
+            "point_mass2d_K1e4_T200": small_config(m, capi, local_rank, "point_mass2d_K1e4_T200"),
+            "point_mass2d_K1e5_T200_closed_loop_1000": closed_loop_config(m, capi, local_rank)}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): 1 core, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -425,10 +699,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--flags", type=int, default=-1,
-                    help="MPPI_FLAG_* bits; default MPPI_FLAG_AUTO_CHAIN: >= 4e5 samples/GPU the one-kernel "
-                         "step (128), >= 1.2e5 fused sampling (32), else the unfused chain with pipelined "
-                         "sampling (512)")
+                    help="MPPI_FLAG_* bits; default MPPI_FLAG_AUTO_CHAIN (the library picks the chain "
+                         "from the shard's shape and reports it in details.flags)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-other-chains", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
+    ap.add_argument("--no-nccl-leg", action="store_true")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="K-shard exchange for --gpus > 1: NVLink peer mailboxes or NCCL")
     args = ap.parse_args()

@@ -93,6 +93,17 @@ extern "C" {
                                                MPPI_FLAG_NO_GRAPH and profiling (those steps run
                                                the plain chain)                               */
 
+#define MPPI_FLAG_TILE_KERNEL     (1u << 10) /* the whole control step as ONE persistent kernel
+                                               that keeps eps ON CHIP: per SM a tile of 64 samples
+                                               is drawn into shared memory, integrated and folded
+                                               into the weighted sums there; eps never reaches
+                                               HBM (mppi_get_info re-draws it on demand: Philox
+                                               is counter based).  Sampled noise, single shard
+                                               or MPPI_COMM_P2P, T*A*(272+16) bytes must fit the
+                                               227 KB of shared memory (T*A <= ~780); otherwise
+                                               the step silently uses the kernel chain.
+                                               Takes precedence over MPPI_FLAG_STEP_KERNEL.   */
+
 /* mppi_params.comm */
 #define MPPI_COMM_NONE  0   /* single shard                                          */
 #define MPPI_COMM_NCCL  1   /* ncclAllReduce(min) for beta, ncclAllReduce(sum) for the
@@ -249,6 +260,11 @@ int mppi_timer_stop(mppi_handle *h, float *elapsed_ms);
  * [MPPI_K_COUNT] (either may be NULL); reading resets the accumulators. */
 int mppi_set_profiling(mppi_handle *h, int enabled);
 int mppi_get_kernel_times(mppi_handle *h, double *ms_sum, int64_t *launches);
+/* MPPI_COMM_P2P: the phases of the LAST step's NVLink exchange on this rank, microseconds from
+ * %globaltimer stamps taken inside the exchanging CTA: us[0] push of this shard's {key,
+ * accumulators} into every peer's mailbox + flags, us[1] wait until every peer's flag has
+ * arrived (= the skew to the slowest rank), us[2] rescale + sum.  Zeros without an exchange. */
+int mppi_get_exchange_times(mppi_handle *h, double us[3]);
 /* total kernels this handle has launched so far (graph replays included) */
 int mppi_get_launch_count(mppi_handle *h, int64_t *launches);
 const char *mppi_kernel_name(int kernel_id);

@@ -30,6 +30,7 @@ FLAG_SPLIT_KERNELS = 1 << 6
 FLAG_STEP_KERNEL = 1 << 7
 FLAG_AUTO_CHAIN = 1 << 8
 FLAG_PIPELINED_SAMPLING = 1 << 9
+FLAG_TILE_KERNEL = 1 << 10
 
 COMM_NONE, COMM_NCCL, COMM_P2P = 0, 1, 2
 MODEL_POINT_MASS, MODEL_LINEAR_AXIS = 0, 1
@@ -43,7 +44,7 @@ EXPORTS = [
     "mppi_step", "mppi_step_enqueue", "mppi_step_wait", "mppi_get_u", "mppi_set_u",
     "mppi_get_info", "mppi_get_flags", "mppi_get_step_info", "mppi_set_noise", "mppi_set_noise_mode",
     "mppi_sample_only", "mppi_shard_range", "mppi_local_samples", "mppi_timer_start", "mppi_timer_stop",
-    "mppi_set_profiling", "mppi_get_kernel_times", "mppi_get_launch_count", "mppi_kernel_name",
+    "mppi_set_profiling", "mppi_get_kernel_times", "mppi_get_exchange_times", "mppi_get_launch_count", "mppi_kernel_name",
     "mppi_comm_unique_id", "mppi_comm_p2p_handle", "mppi_comm_p2p_connect", "mppi_last_error",
     "mppi_abi_version",
 ]
@@ -132,6 +133,7 @@ def load():
     L.mppi_set_profiling.argtypes = [H, C.c_int]
     L.mppi_get_kernel_times.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.mppi_get_launch_count.argtypes = [H, C.POINTER(C.c_int64)]
+    L.mppi_get_exchange_times.argtypes = [H, C.POINTER(C.c_double)]
     L.mppi_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.mppi_comm_p2p_handle.argtypes = [H, C.POINTER(C.c_uint8)]
     L.mppi_comm_p2p_connect.argtypes = [H, C.POINTER(C.c_uint8)]

@@ -164,6 +164,12 @@ class PointMassModel:
         return {self._lib.mppi_kernel_name(i).decode(): (float(ms[i]), int(n[i]))
                 for i in range(capi.K_COUNT)}
 
+    def exchange_times(self):
+        """MPPI_COMM_P2P: {push, wait, merge} microseconds of the last step's NVLink exchange."""
+        us = (C.c_double * 3)()
+        capi.check(self._lib.mppi_get_exchange_times(self._h, us))
+        return {"push_us": float(us[0]), "wait_slowest_us": float(us[1]), "merge_us": float(us[2])}
+
     def launch_count(self):
         n = C.c_int64()
         capi.check(self._lib.mppi_get_launch_count(self._h, C.byref(n)))

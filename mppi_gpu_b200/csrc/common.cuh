@@ -41,6 +41,8 @@ struct CtlDev {
     unsigned int done;            // CTA ticket counter of the merged average+finalize kernel
     unsigned int comm_error;      // set when a peer-mailbox wait timed out
     unsigned int pad_;
+    unsigned long long t_xchg[4]; // %globaltimer (ns) of the last K-shard exchange: push begins,
+                                  // own data + flags out, every peer's flag seen, merged
 };
 
 constexpr unsigned long long kMinKeyInit = ~0ull;
@@ -235,10 +237,12 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 }
 #endif  // __CUDACC__
 
-// Peer mailbox of one rank: slot s is written only by rank s (over NVLink for s != self).
-//   [0] key_seq  [1] key  [2] acc_seq  [3] reserved  [4 ...] acc[R+1]
+// Peer mailbox of one rank: two buffers (parity of the step number) of one slot per sender;
+// slot s is written only by rank s (over NVLink for s != self).
+//   [0] seq (single exchange) / key_seq  [1] key  [2] acc_seq  [3] reserved  [4 ...] acc[R+1]
 constexpr int kMailboxHeaderWords = 4;
 constexpr int kMaxWorld = 16;
+constexpr int kMailboxBuffers = 2;
 inline size_t mailbox_slot_words(int rows)
 {
     return (size_t)((kMailboxHeaderWords + rows + 1 + 15) / 16 * 16);     // 128-byte multiple

@@ -67,6 +67,8 @@ struct mppi_handle {
     ProblemDev h_prob{};
     float *h_stage = nullptr;     // pinned [kStageSlots][2*kMaxAct]
     int stage_slot = 0;
+    bool stage_used[kStageSlots] = {};
+    unsigned long long stage_tag[kStageSlots] = {};   // steps enqueued when the slot was staged
     float *h_next = nullptr;      // pinned + mapped [kNextFloats]: next action, error flag, step seq
     unsigned long long steps_enqueued = 0;   // == the seq the last enqueued step will publish
 
@@ -97,6 +99,12 @@ struct mppi_handle {
     bool peers_are_ipc = false;                           // peer_mb[] came from cudaIpcOpenMemHandle
     std::vector<mppi_handle *> children;                  // single-process multi-device group
 
+    bool step_ok = false, tile_ok = false;   // the one-kernel variants this shape supports
+    // the last step kept eps on chip (tile kernel): the get_inf tap re-draws it for this Philox
+    // step index before reading d_eps
+    bool eps_on_chip = false;
+    unsigned long long eps_step = 0;
+
     bool problem_set = false;
     bool injected = false;
     bool profiling = false;
@@ -116,10 +124,17 @@ bool multi(const mppi_handle *h) { return h->p.world_size > 1; }
 bool p2p(const mppi_handle *h) { return multi(h) && h->p.comm == MPPI_COMM_P2P; }
 bool fused(const mppi_handle *h) { return (h->p.flags & MPPI_FLAG_FUSED_SAMPLING) != 0; }
 // the one-kernel step: sampled noise, single shard, row sums fit in shared memory
+// the on-chip tile kernel (tile.cu): same conditions, takes precedence over the step kernel
+bool tile_step(const mppi_handle *h, bool sample)
+{
+    return sample && (h->p.flags & MPPI_FLAG_TILE_KERNEL) && (!multi(h) || p2p(h)) &&
+           !(h->p.flags & MPPI_FLAG_SPLIT_KERNELS) && h->d_part != nullptr && h->tile_ok;
+}
 bool one_kernel(const mppi_handle *h, bool sample)
 {
+    if (tile_step(h, sample)) return true;
     return sample && (h->p.flags & MPPI_FLAG_STEP_KERNEL) && (!multi(h) || p2p(h)) &&
-           !(h->p.flags & MPPI_FLAG_SPLIT_KERNELS) && h->d_part != nullptr;
+           !(h->p.flags & MPPI_FLAG_SPLIT_KERNELS) && h->d_part != nullptr && h->step_ok;
 }
 
 // pipelined sampling applies to the sampled, unfused, graph-replayed chain only
@@ -166,13 +181,16 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
     CK(mark());
     if (one_kernel(h, sample)) {
         for (int i = 0; i < MPPI_K_AVERAGE; ++i) CK(mark());     // the time is booked on "average"
-        CK(launch_step(c, h->tmap_st, h->d_eps, h->d_U, h->d_prob, h->d_S, h->d_ctl, h->d_part,
-                       h->d_acc, h->d_Uprev, h->d_next, h->p.flags, !multi(h)));
+        // K-shards: the last CTA of the kernel also runs the NVLink exchange (xchg.cuh) -- one
+        // kernel per step for any number of GPUs
+        const XchgArgs xa = make_xchg_args(h->peer_mb, h->p.rank, p2p(h) ? h->p.world_size : 1, h->R);
+        if (tile_step(h, sample))
+            CK(launch_tile(c, h->d_U, h->d_prob, h->d_S, h->d_ctl, h->d_part, h->d_Uprev, h->d_next,
+                           h->p.flags, xa));
+        else
+            CK(launch_step(c, h->tmap_st, h->d_eps, h->d_U, h->d_prob, h->d_S, h->d_ctl, h->d_part,
+                           h->d_Uprev, h->d_next, h->p.flags, xa));
         CK(mark());
-        if (p2p(h))
-            CK(launch_xchg_merge_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl,
-                                          h->d_next, h->p.flags, h->peer_mb, h->p.rank,
-                                          h->p.world_size));
         CK(mark());
         CK(mark());
         return MPPI_OK;
@@ -188,8 +206,9 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
     // exchange); NCCL shards all-reduce beta first (two exchanges)
     const bool split = (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) != 0;
     const bool one_xchg = p2p(h) && !split;
+    const XchgArgs xa = make_xchg_args(h->peer_mb, h->p.rank, p2p(h) ? h->p.world_size : 1, h->R);
     if (p2p(h) && !one_xchg) {
-        CK(launch_xchg_min(c, h->d_ctl, h->peer_mb, h->p.rank, h->p.world_size));
+        CK(launch_xchg_min(c, h->d_ctl, xa));
     } else if (multi(h) && !p2p(h)) {
         if (!h->comm.allreduce_min_u64(&h->d_ctl->min_key, 1, c.stream, err))
             return fail(MPPI_ERR_COMM, "%s", err.c_str());
@@ -203,11 +222,11 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
     CK(mark());
     if (one_xchg) {
         CK(launch_xchg_merge_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
-                                      h->p.flags, h->peer_mb, h->p.rank, h->p.world_size));
+                                      h->p.flags, xa));
     } else if (p2p(h)) {
         // exchange + integer sum + U update in one kernel over peer memory
         CK(launch_xchg_sum_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
-                                    h->p.flags, h->peer_mb, h->p.rank, h->p.world_size));
+                                    h->p.flags, xa));
     } else if (multi(h)) {
         if (!h->comm.allreduce_sum_i64(h->d_acc, (size_t)h->R + 1, c.stream, err))
             return fail(MPPI_ERR_COMM, "%s", err.c_str());
@@ -224,7 +243,7 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
 
 int kernels_per_step(const mppi_handle *h, bool sample)
 {
-    if (one_kernel(h, sample)) return multi(h) ? 2 : 1;
+    if (one_kernel(h, sample)) return 1;            // K-shards exchange inside the same kernel
     int n = 2;                                  // rollout, average(+weights,+finalize)
     if (sample && !fused(h)) n += 1;            // sampling
     if (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) n += 1;      // separate weights kernel
@@ -524,12 +543,14 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     const size_t eps_bytes = sizeof(float) * (size_t)h->R * (size_t)c.k_pad;
     CKH(cudaMalloc(&h->d_eps, eps_bytes));
     CKH(cudaMalloc(&h->d_S, sizeof(float) * (size_t)c.k_pad));
-    CKH(cudaMalloc(&h->d_wt, sizeof(float) * (size_t)c.k_pad));
+    if (p.flags & MPPI_FLAG_SPLIT_KERNELS)     // the materialised weights of the split chain only
+        CKH(cudaMalloc(&h->d_wt, sizeof(float) * (size_t)c.k_pad));
     CKH(cudaMalloc(&h->d_acc, sizeof(long long) * ((size_t)h->R + 1)));
     CKH(cudaMalloc(&h->d_U, sizeof(float) * (size_t)h->R));
     CKH(cudaMalloc(&h->d_Uprev, sizeof(float) * (size_t)h->R));
     if (p.world_size > 1 && p.comm == MPPI_COMM_P2P) {
-        const size_t mb_bytes = sizeof(unsigned long long) * mailbox_slot_words(h->R) * p.world_size;
+        const size_t mb_bytes = sizeof(unsigned long long) * mailbox_slot_words(h->R) * p.world_size *
+                                kMailboxBuffers;
         CKH(cudaMalloc(&h->d_mailbox, mb_bytes));
         CKH(cudaMemsetAsync(h->d_mailbox, 0, mb_bytes, h->stream));
         h->peer_mb[p.rank] = h->d_mailbox;
@@ -544,7 +565,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     // pad columns finite and defines injected-noise mode before the first mppi_set_noise.
     CKH(cudaMemsetAsync(h->d_eps, 0, eps_bytes, h->stream));
     CKH(cudaMemsetAsync(h->d_S, 0, sizeof(float) * (size_t)c.k_pad, h->stream));
-    CKH(cudaMemsetAsync(h->d_wt, 0, sizeof(float) * (size_t)c.k_pad, h->stream));
+    if (h->d_wt) CKH(cudaMemsetAsync(h->d_wt, 0, sizeof(float) * (size_t)c.k_pad, h->stream));
     CKH(cudaMemsetAsync(h->d_acc, 0, sizeof(long long) * ((size_t)h->R + 1), h->stream));
     CKH(cudaMemsetAsync(h->d_U, 0, sizeof(float) * (size_t)h->R, h->stream));
     CKH(cudaMemsetAsync(h->d_Uprev, 0, sizeof(float) * (size_t)h->R, h->stream));
@@ -552,6 +573,15 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     for (auto &e : h->ev) CKH(cudaEventCreate(&e));
     CKH(cudaEventCreate(&h->t0));
     CKH(cudaEventCreate(&h->t1));
+    {
+        size_t need = 0, have = 0;
+        if (const char *k = check_smem_requirements(c, &need, &have)) {
+            rc = fail(MPPI_ERR_INVALID, "horizon %d x act_dim %d: %s needs %zu bytes of shared memory, "
+                      "the device offers %zu per block", p.horizon, p.act_dim, k, need, have);
+            mppi_destroy(h);
+            return rc;
+        }
+    }
     CKH(configure_kernels(c));
     if (p.flags & MPPI_FLAG_AUTO_CHAIN) {
         // thresholds measured on B200 at T=200 (tools/quick_prof.py): the one-kernel step wins once
@@ -569,7 +599,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
         h->p.flags &= ~MPPI_FLAG_AUTO_CHAIN;
     }
     if ((h->p.flags & MPPI_FLAG_PIPELINED_SAMPLING) &&
-        !(h->p.flags & (MPPI_FLAG_FUSED_SAMPLING | MPPI_FLAG_STEP_KERNEL))) {
+        !(h->p.flags & (MPPI_FLAG_FUSED_SAMPLING | MPPI_FLAG_STEP_KERNEL | MPPI_FLAG_TILE_KERNEL))) {
         int least = 0, greatest = 0;
         CKH(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         CKH(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, least));
@@ -580,8 +610,13 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
         h->eps_base[1] = h->d_eps_alt;
         CKH(cudaMemsetAsync(h->d_eps_alt, 0, eps_bytes, h->stream));
     }
-    if ((h->p.flags & MPPI_FLAG_STEP_KERNEL) && step_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms)) {
-        CKH(configure_step(c));
+    h->step_ok = (h->p.flags & MPPI_FLAG_STEP_KERNEL) &&
+                 step_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms);
+    h->tile_ok = (h->p.flags & MPPI_FLAG_TILE_KERNEL) &&
+                 tile_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms);
+    if (h->step_ok) CKH(configure_step(c));
+    if (h->tile_ok) CKH(configure_tile(c));
+    if (h->step_ok || h->tile_ok) {
         CKH(cudaMalloc(&h->d_part, sizeof(float) * step_part_floats(c)));
         CKH(cudaMemsetAsync(h->d_part, 0, sizeof(float) * step_part_floats(c), h->stream));
     }
@@ -766,6 +801,18 @@ int mppi_set_state(mppi_handle *h, const float *x)
     int rc = check_handle(h);
     if (rc) return rc;
     if (!x) return fail(MPPI_ERR_INVALID, "null argument");
+    // A staging slot may be rewritten once its async copy has run.  The copy of a slot staged
+    // when `tag` steps had been enqueued precedes step tag+1 on the stream, so it is done as
+    // soon as that step has published its sequence number (mapped host memory, no API call);
+    // otherwise -- no step behind it yet, or still running -- settle it the slow way.  Only
+    // reached after kStageSlots set_state calls without a finished step in between.
+    if (h->stage_used[h->stage_slot]) {
+        const unsigned long long seen = __atomic_load_n(
+            reinterpret_cast<unsigned long long *>(h->h_next + kNextSeqOffset), __ATOMIC_ACQUIRE);
+        if (seen < h->stage_tag[h->stage_slot] + 1) CK(cudaStreamSynchronize(h->stream));
+    }
+    h->stage_used[h->stage_slot] = true;
+    h->stage_tag[h->stage_slot] = h->steps_enqueued;
     float *slot = h->h_stage + (size_t)h->stage_slot * 2 * kMaxAct;
     h->stage_slot = (h->stage_slot + 1) % kStageSlots;
     for (int i = 0; i < h->S; ++i) { slot[i] = x[i]; h->h_prob.x0[i] = x[i]; }
@@ -815,6 +862,7 @@ int mppi_step_enqueue(mppi_handle *h)
         CK(launch_sample(side, h->d_eps_alt, h->d_ctl, true, h->steps_enqueued + 1));
         CK(cudaEventRecord(h->ev_sampled, h->stream2));
         h->eps_last = h->d_eps;
+        h->eps_on_chip = false;
         std::swap(h->d_eps, h->d_eps_alt);
         std::swap(h->tmap, h->tmap_alt);
         std::swap(h->tmap_ro, h->tmap_ro_alt);
@@ -828,6 +876,8 @@ int mppi_step_enqueue(mppi_handle *h)
     // (the plain chain draws the same values again)
     if ((rc = leave_pipeline(h)) != MPPI_OK) return rc;
     h->eps_last = h->d_eps;
+    h->eps_on_chip = tile_step(h, sample);
+    h->eps_step = h->steps_enqueued;          // the Philox step index this step draws with
     if (h->profiling || (h->p.flags & MPPI_FLAG_NO_GRAPH)) {
         rc = enqueue_chain(h, sample, h->profiling ? h->ev : nullptr);
         if (rc) return rc;
@@ -885,7 +935,7 @@ int mppi_step_wait(mppi_handle *h, float *next_act)
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
             const bool split = (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) != 0;
-            const bool ran = h->prof_one_kernel ? (i == MPPI_K_AVERAGE || (i == MPPI_K_COMM_SUM && multi(h)))
+            const bool ran = h->prof_one_kernel ? (i == MPPI_K_AVERAGE)
                            : (i == MPPI_K_SAMPLE) ? (sample && !fused(h))
                            : (i == MPPI_K_COMM_MIN) ? (multi(h) && (!p2p(h) || split))
                            : (i == MPPI_K_COMM_SUM) ? multi(h)
@@ -894,10 +944,13 @@ int mppi_step_wait(mppi_handle *h, float *next_act)
             if (ran) { h->ms_sum[i] += ms; h->launches[i] += 1; }
         }
     }
+    // a failed exchange has not touched U and has published no action: nothing is copied to
+    // the caller, and the handle (and its peers') is unusable from here on
+    if (h->h_next[kMaxAct] != 0.0f)
+        return fail(MPPI_ERR_COMM, "peer-mailbox exchange timed out (a rank did not arrive); "
+                                   "U was left unchanged, the handle cannot be used any further");
     if (next_act)
         for (int a = 0; a < h->p.act_dim; ++a) next_act[a] = h->h_next[a];
-    if (h->h_next[kMaxAct] != 0.0f)
-        return fail(MPPI_ERR_COMM, "peer-mailbox exchange timed out (a rank did not arrive)");
     return MPPI_OK;
 }
 
@@ -986,6 +1039,12 @@ int mppi_get_info(mppi_handle *h, float *x, float *u, float *e, float *cost, flo
                         cudaGetErrorString(e__));                                         \
         }                                                                                 \
     } while (0)
+    if ((e || x) && h->eps_on_chip) {
+        // the last step kept its noise in shared memory: draw it again (counter based: same bits)
+        CKS(launch_sample(c, h->d_eps, h->d_ctl, true, h->eps_step));
+        h->total_launches += 1;
+        h->eps_on_chip = false;               // d_eps now holds that step's noise
+    }
     if (weight) {
         CKS(cudaMalloc(&scratch, sizeof(float) * (size_t)c.k_local));
         CKS(launch_norm_weights(c, h->d_S, h->p.lambda, info.beta, info.eta, scratch));
@@ -1042,6 +1101,7 @@ int mppi_set_noise(mppi_handle *h, const float *e)
     const size_t n = (size_t)c.k_local * h->R;
     if ((rc = leave_pipeline(h)) != MPPI_OK) return rc;   // d_eps may be receiving noise drawn ahead
     h->eps_last = h->d_eps;
+    h->eps_on_chip = false;
     float *scratch = nullptr;
     CK(cudaMalloc(&scratch, sizeof(float) * n));
     cudaError_t err = cudaMemcpyAsync(scratch, e, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream);
@@ -1065,6 +1125,7 @@ int mppi_sample_only(mppi_handle *h, uint64_t step)
     CK(cudaStreamSynchronize(h->stream));
     if ((rc = leave_pipeline(h)) != MPPI_OK) return rc;
     h->eps_last = h->d_eps;                              // what get_inf returns next
+    h->eps_on_chip = false;
     CK(launch_sample(h->ctx, h->d_eps, h->d_ctl, true, step));
     CK(cudaStreamSynchronize(h->stream));
     h->total_launches += 1;
@@ -1117,6 +1178,23 @@ int mppi_get_kernel_times(mppi_handle *h, double *ms_sum, int64_t *launches)
         h->ms_sum[i] = 0.0;
         h->launches[i] = 0;
     }
+    return MPPI_OK;
+}
+
+int mppi_get_exchange_times(mppi_handle *h, double us[3])
+{
+    if (h && !h->children.empty()) return mppi_get_exchange_times(h->children[0], us);
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!us) return fail(MPPI_ERR_INVALID, "null argument");
+    CtlDev ctl;
+    CK(cudaMemcpyAsync(&ctl, h->d_ctl, sizeof ctl, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    us[0] = us[1] = us[2] = 0.0;
+    if (!p2p(h) || ctl.t_xchg[3] == 0) return MPPI_OK;
+    us[0] = (double)(ctl.t_xchg[1] - ctl.t_xchg[0]) * 1e-3;   // push own data + flags
+    us[1] = (double)(ctl.t_xchg[2] - ctl.t_xchg[1]) * 1e-3;   // wait for the slowest peer
+    us[2] = (double)(ctl.t_xchg[3] - ctl.t_xchg[2]) * 1e-3;   // rescale + sum
     return MPPI_OK;
 }
 

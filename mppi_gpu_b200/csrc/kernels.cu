@@ -643,44 +643,29 @@ finalize_kernel(long long *__restrict__ acc, float *__restrict__ U, float *__res
 }
 
 // =================================================================================
-// K-shard exchange over NVLink peer memory (MPPI_COMM_P2P): every rank owns a mailbox with
-// one slot per sender; a sender stores its contribution straight into every peer's mailbox
-// (st.relaxed.sys), fences, then publishes a sequence number (st.release.sys); the owner
-// polls its own memory (ld.acquire.sys).  Sequence = control step + 1, so nothing is ever
-// reset and a stale flag can never match.  Replaces the two latency-bound NCCL all-reduces
-// (one kernel launch + ~20-30 us each at 8 ranks) with two single-CTA kernels, the second of
-// which also performs the U update.  A bounded spin (about a second) turns a dead peer into
-// an error code instead of a hang.
+// K-shard exchange over NVLink peer memory (MPPI_COMM_P2P) as kernels of their own, behind
+// average_kernel.  Protocol, double buffering and the single-exchange merge: xchg.cuh (the
+// one-kernel steps run the same code in their last CTA).  A bounded spin (about two seconds)
+// turns a dead peer into an error code instead of a hang; a failed exchange leaves U untouched.
 // =================================================================================
-struct PeerTable {
-    unsigned long long *mb[kMaxWorld];     // mailbox base of every rank, as mapped in THIS process
-};
+constexpr int kXchgThreads = 512;
 
-__device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigned long long seq)
-{
-    const long long t0 = clock64();
-    while (ld_acquire_sys_u64(flag) != seq) {
-        if (clock64() - t0 > 4000000000ll) return false;      // ~2 s at 2 GHz
-        __nanosleep(64);
-    }
-    return true;
-}
-
-// (3a) beta = min over all shards of the packed (cost, index) key
+// (3a) beta = min over all shards of the packed (cost, index) key -- MPPI_FLAG_SPLIT_KERNELS only
 __global__ void __launch_bounds__(32)
-xchg_min_kernel(CtlDev *__restrict__ ctl, const __grid_constant__ PeerTable peers, int rank,
-                int world, size_t slot_words)
+xchg_min_kernel(CtlDev *__restrict__ ctl, const __grid_constant__ XchgArgs xa)
 {
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x, rank = xa.rank, world = xa.world;
+    const size_t sw = (size_t)xa.slot_words;
     const unsigned long long seq = ctl->step + 1;
+    const int par = (int)(seq & 1ull);
     const unsigned long long mine = ctl->min_key;
     unsigned long long key = kMinKeyInit;
     if (lane < world) {
-        unsigned long long *slot = peers.mb[lane] + (size_t)rank * slot_words;   // my slot at peer
+        unsigned long long *slot = mb_slot(xa.peers.mb[lane], par, world, rank, sw);   // my slot at peer
         st_relaxed_sys_u64(slot + 1, mine);
         __threadfence_system();
         st_release_sys_u64(slot + 0, seq);
-        const unsigned long long *in = peers.mb[rank] + (size_t)lane * slot_words;  // lane's slot here
+        const unsigned long long *in = mb_slot(xa.peers.mb[rank], par, world, lane, sw);  // lane's slot here
         if (wait_seq(in + 0, seq)) key = ld_relaxed_sys_u64(in + 1);
         else atomicExch(&ctl->comm_error, 1u);
     }
@@ -689,36 +674,46 @@ xchg_min_kernel(CtlDev *__restrict__ ctl, const __grid_constant__ PeerTable peer
 }
 
 // (5') all-reduce(sum) of the fixed-point accumulators through the mailboxes, then finalize
-__global__ void __launch_bounds__(256)
+//      (the second exchange of the MPPI_FLAG_SPLIT_KERNELS flow)
+__global__ void __launch_bounds__(kXchgThreads)
 xchg_sum_finalize_kernel(long long *__restrict__ acc, float *__restrict__ U,
                          float *__restrict__ U_prev, const ProblemDev *__restrict__ prob,
                          CtlDev *__restrict__ ctl, float *__restrict__ next_act, int T, int A,
-                         unsigned flags, const __grid_constant__ PeerTable peers, int rank, int world,
-                         size_t slot_words)
+                         unsigned flags, const __grid_constant__ XchgArgs xa)
 {
     extern __shared__ float s_u[];
-    const int R = T * A;
+    const int R = T * A, rank = xa.rank, world = xa.world;
+    const size_t sw = (size_t)xa.slot_words;
     const unsigned long long seq = ctl->step + 1;
+    const int par = (int)(seq & 1ull);
     // push my accumulators into every peer's mailbox (including my own)
     for (int r = 0; r < world; ++r) {
-        unsigned long long *slot = peers.mb[r] + (size_t)rank * slot_words + kMailboxHeaderWords;
+        unsigned long long *slot = mb_slot(xa.peers.mb[r], par, world, rank, sw) + kMailboxHeaderWords;
         for (int i = threadIdx.x; i <= R; i += blockDim.x)
             st_relaxed_sys_u64(slot + i, (unsigned long long)acc[i]);
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x < world) {
-        st_release_sys_u64(peers.mb[threadIdx.x] + (size_t)rank * slot_words + 2, seq);
-        const unsigned long long *in = peers.mb[rank] + (size_t)threadIdx.x * slot_words;
+        st_release_sys_u64(mb_slot(xa.peers.mb[threadIdx.x], par, world, rank, sw) + 2, seq);
+        const unsigned long long *in = mb_slot(xa.peers.mb[rank], par, world, threadIdx.x, sw);
         if (!wait_seq(in + 2, seq)) atomicExch(&ctl->comm_error, 1u);
     }
     __syncthreads();
+    if (*reinterpret_cast<volatile unsigned int *>(&ctl->comm_error)) {
+        if (threadIdx.x == 0) publish_comm_error(ctl, next_act);
+        return;
+    }
     // integer sum in rank order (exact: any order gives the same bits)
+    unsigned long long *my = xa.peers.mb[rank] + (size_t)par * world * sw;
     for (int i = threadIdx.x; i <= R; i += blockDim.x) {
+        long long v[kMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            v[r] = r < world ? (long long)ld_relaxed_sys_u64(my + (size_t)r * sw + kMailboxHeaderWords + i) : 0ll;
         long long sum = 0;
-        for (int r = 0; r < world; ++r)
-            sum += (long long)ld_relaxed_sys_u64(peers.mb[rank] + (size_t)r * slot_words +
-                                                 kMailboxHeaderWords + i);
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r) sum += v[r];
         acc[i] = sum;
     }
     __threadfence();
@@ -726,65 +721,35 @@ xchg_sum_finalize_kernel(long long *__restrict__ acc, float *__restrict__ U,
     finalize_body(acc, U, U_prev, prob, ctl, next_act, T, A, flags, s_u);
 }
 
-// (3a+5'') ONE exchange per step: every shard has averaged with ITS OWN minimum beta_r as the
-// softmax reference (no beta exchange before the average), so acc_r = sum_k w~_k eps_k and
-// eta_r are relative to beta_r.  Each rank pushes {key_r, acc_r} to every peer, takes the
-// global minimum key, rescales every shard's accumulators by exp(-(beta_r - beta)/lambda) and
-// sums them in rank order -- the same arithmetic on the same bits on every rank, so the
-// replicated U stays bit-identical -- then applies the U update.  (The online-softmax merge
-// the one-kernel step uses between CTAs, applied between GPUs.)
-__global__ void __launch_bounds__(256)
+// (3a+5'') ONE exchange per step behind average_kernel: xchg_merge_body on the shard's
+// accumulators (relative to its own minimum), then the U update.  Shared memory:
+// [R+1] int64 accumulators, [R] floats U_new, [kMaxWorld+1] doubles.
+__global__ void __launch_bounds__(kXchgThreads)
 xchg_merge_finalize_kernel(long long *__restrict__ acc, float *__restrict__ U,
                            float *__restrict__ U_prev, const ProblemDev *__restrict__ prob,
                            CtlDev *__restrict__ ctl, float *__restrict__ next_act, int T, int A,
-                           unsigned flags, const __grid_constant__ PeerTable peers, int rank,
-                           int world, size_t slot_words)
+                           unsigned flags, const __grid_constant__ XchgArgs xa)
 {
-    extern __shared__ float s_u[];
-    __shared__ double s_f[kMaxWorld];
+    extern __shared__ __align__(16) uint8_t s_x[];
     const int R = T * A;
-    const unsigned long long seq = ctl->step + 1;
-    const unsigned long long mine = ctl->min_key;
-    for (int r = 0; r < world; ++r) {
-        unsigned long long *slot = peers.mb[r] + (size_t)rank * slot_words;
-        if (threadIdx.x == 0) st_relaxed_sys_u64(slot + 1, mine);
-        for (int i = threadIdx.x; i <= R; i += blockDim.x)
-            st_relaxed_sys_u64(slot + kMailboxHeaderWords + i, (unsigned long long)acc[i]);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < world) {
-        st_release_sys_u64(peers.mb[threadIdx.x] + (size_t)rank * slot_words + 2, seq);
-        const unsigned long long *in = peers.mb[rank] + (size_t)threadIdx.x * slot_words;
-        if (!wait_seq(in + 2, seq)) atomicExch(&ctl->comm_error, 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long gkey = kMinKeyInit;
-        for (int r = 0; r < world; ++r) {
-            const unsigned long long k = ld_relaxed_sys_u64(peers.mb[rank] + (size_t)r * slot_words + 1);
-            gkey = k < gkey ? k : gkey;
-        }
-        const float beta = ordered_to_float((uint32_t)(gkey >> 32));
-        const float nil = prob->neg_inv_lambda;
-        for (int r = 0; r < world; ++r) {
-            const unsigned long long k = ld_relaxed_sys_u64(peers.mb[rank] + (size_t)r * slot_words + 1);
-            const float beta_r = ordered_to_float((uint32_t)(k >> 32));
-            s_f[r] = k == kMinKeyInit ? 0.0 : (double)expf(__fmul_rn(nil, __fsub_rn(beta_r, beta)));
-        }
-        ctl->min_key = gkey;                      // beta / argmin of the whole step
-    }
-    __syncthreads();
+    long long *s_acc = reinterpret_cast<long long *>(s_x);
+    double *s_f = reinterpret_cast<double *>(s_acc + (R + 1));
+    float *s_u = reinterpret_cast<float *>(s_f + kMaxWorld + 1);
     for (int i = threadIdx.x; i <= R; i += blockDim.x) {
-        double sum = 0.0;
-        for (int r = 0; r < world; ++r)
-            sum += (double)(long long)ld_relaxed_sys_u64(peers.mb[rank] + (size_t)r * slot_words +
-                                                         kMailboxHeaderWords + i) * s_f[r];
-        acc[i] = __double2ll_rn(sum);
+        s_acc[i] = acc[i];
+        acc[i] = 0;                                // the global accumulators are re-armed here
     }
-    __threadfence();
     __syncthreads();
-    finalize_body(acc, U, U_prev, prob, ctl, next_act, T, A, flags, s_u);
+    if (!xchg_merge_body(s_acc, R, prob, ctl, xa, s_f, (int)blockDim.x, 0)) {
+        if (threadIdx.x == 0) publish_comm_error(ctl, next_act);
+        return;
+    }
+    finalize_body(s_acc, U, U_prev, prob, ctl, next_act, T, A, flags, s_u);
+}
+
+size_t xchg_merge_smem_bytes(int R)
+{
+    return (size_t)(R + 1) * 8 + (size_t)(kMaxWorld + 1) * 8 + (size_t)R * 4;
 }
 
 // =================================================================================
@@ -881,6 +846,7 @@ trajectories_kernel(const float *__restrict__ eps, size_t ld, long long k_local,
 
 __global__ void clear_ctl_kernel(CtlDev *ctl)
 {
+    for (int i = 0; i < 4; ++i) ctl->t_xchg[i] = 0;
     ctl->min_key = kMinKeyInit;
     ctl->last_key = kMinKeyInit;
     ctl->step = 0;
@@ -1002,24 +968,6 @@ cudaError_t launch_rollout_tma(const LaunchCtx &c, const CUtensorMap &tmap, cons
     return cudaSuccess;
 }
 
-template <int A, class MODEL, int W>
-static cudaError_t configure_rollout_tma_w(int T)
-{
-    return cudaFuncSetAttribute(rollout_tma_kernel<A, MODEL, W>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)rollout_tma_smem_bytes<A>(T, W));
-}
-template <int A>
-static cudaError_t configure_rollout_tma(int T)
-{
-    cudaError_t e;
-    MPPI_FOR_EACH_MODEL(
-        if ((e = configure_rollout_tma_w<A, kM, 64>(T)) != cudaSuccess) return e;
-        if ((e = configure_rollout_tma_w<A, kM, 128>(T)) != cudaSuccess) return e;
-        if ((e = configure_rollout_tma_w<A, kM, 256>(T)) != cudaSuccess) return e);
-    return cudaSuccess;
-}
-
 int rollout_tma_rows(int A)
 {
     switch (A) {
@@ -1068,40 +1016,38 @@ cudaError_t launch_finalize(const LaunchCtx &c, long long *acc, float *U, float 
     return cudaGetLastError();
 }
 
-cudaError_t launch_xchg_min(const LaunchCtx &c, CtlDev *ctl, unsigned long long *const *peer_mb,
-                            int rank, int world)
+XchgArgs make_xchg_args(unsigned long long *const *peer_mb, int rank, int world, int rows)
 {
-    PeerTable pt{};
-    for (int r = 0; r < world; ++r) pt.mb[r] = peer_mb[r];
-    xchg_min_kernel<<<1, 32, 0, c.stream>>>(ctl, pt, rank, world, mailbox_slot_words(c.rows));
+    XchgArgs xa{};
+    xa.rank = rank;
+    xa.world = world;
+    xa.slot_words = (unsigned long long)mailbox_slot_words(rows);
+    for (int r = 0; r < world && r < kMaxWorld; ++r) xa.peers.mb[r] = peer_mb ? peer_mb[r] : nullptr;
+    return xa;
+}
+
+cudaError_t launch_xchg_min(const LaunchCtx &c, CtlDev *ctl, const XchgArgs &xa)
+{
+    xchg_min_kernel<<<1, 32, 0, c.stream>>>(ctl, xa);
     return cudaGetLastError();
 }
 
 cudaError_t launch_xchg_sum_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
                                      const ProblemDev *prob, CtlDev *ctl, float *next_act,
-                                     unsigned flags, unsigned long long *const *peer_mb, int rank,
-                                     int world)
+                                     unsigned flags, const XchgArgs &xa)
 {
-    PeerTable pt{};
-    for (int r = 0; r < world; ++r) pt.mb[r] = peer_mb[r];
     const size_t smem = sizeof(float) * (size_t)c.rows;
-    xchg_sum_finalize_kernel<<<1, 256, smem, c.stream>>>(acc, U, U_prev, prob, ctl, next_act,
-                                                         c.horizon, c.act_dim, flags, pt, rank,
-                                                         world, mailbox_slot_words(c.rows));
+    xchg_sum_finalize_kernel<<<1, kXchgThreads, smem, c.stream>>>(acc, U, U_prev, prob, ctl, next_act,
+                                                                  c.horizon, c.act_dim, flags, xa);
     return cudaGetLastError();
 }
 
 cudaError_t launch_xchg_merge_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
                                        const ProblemDev *prob, CtlDev *ctl, float *next_act,
-                                       unsigned flags, unsigned long long *const *peer_mb, int rank,
-                                       int world)
+                                       unsigned flags, const XchgArgs &xa)
 {
-    PeerTable pt{};
-    for (int r = 0; r < world; ++r) pt.mb[r] = peer_mb[r];
-    const size_t smem = sizeof(float) * (size_t)c.rows;
-    xchg_merge_finalize_kernel<<<1, 256, smem, c.stream>>>(acc, U, U_prev, prob, ctl, next_act,
-                                                           c.horizon, c.act_dim, flags, pt, rank,
-                                                           world, mailbox_slot_words(c.rows));
+    xchg_merge_finalize_kernel<<<1, kXchgThreads, xchg_merge_smem_bytes(c.rows), c.stream>>>(
+        acc, U, U_prev, prob, ctl, next_act, c.horizon, c.act_dim, flags, xa);
     return cudaGetLastError();
 }
 
@@ -1140,62 +1086,78 @@ cudaError_t launch_trajectories(const LaunchCtx &c, const float *eps, const floa
     return cudaGetLastError();
 }
 
-// Per-device one-time opt-in to large dynamic shared memory (called from mppi_create).
+// Opt-in to large dynamic shared memory.  cudaFuncAttributeMaxDynamicSharedMemorySize is a
+// property of the FUNCTION on the device, not of a handle: it is always set to the device's
+// opt-in maximum, never to what one handle needs, so that controllers with different horizons can
+// live side by side in one process (a smaller value set by a later handle would make an earlier
+// handle's next launch fail).  What a handle needs is validated against that maximum
+// (check_smem_requirements).
+constexpr int kSmemOptIn = 227 * 1024;      // sm_100: 232448 bytes per block, static + dynamic
+constexpr int kSmemStaticSlack = 256;       // the kernels' few static words (keys, flags)
+
+template <class K>
+static cudaError_t opt_in(K kernel)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kSmemOptIn - (int)fa.sharedSizeBytes);
+}
+
 template <int A, class MODEL>
-static cudaError_t configure_rollout_s(int smem)
+static cudaError_t configure_rollout_s()
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(rollout_kernel<A, MODEL, true, 4>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rollout_kernel<A, MODEL, false, 4>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rollout_kernel<A, MODEL, false, 2>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(rollout_kernel<A, MODEL, false, 1>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if ((e = opt_in(rollout_kernel<A, MODEL, true, 4>)) != cudaSuccess) return e;
+    if ((e = opt_in(rollout_kernel<A, MODEL, false, 4>)) != cudaSuccess) return e;
+    if ((e = opt_in(rollout_kernel<A, MODEL, false, 2>)) != cudaSuccess) return e;
+    if ((e = opt_in(rollout_kernel<A, MODEL, false, 1>)) != cudaSuccess) return e;
+    if ((e = opt_in(rollout_tma_kernel<A, MODEL, 64>)) != cudaSuccess) return e;
+    if ((e = opt_in(rollout_tma_kernel<A, MODEL, 128>)) != cudaSuccess) return e;
+    return opt_in(rollout_tma_kernel<A, MODEL, 256>);
 }
 template <int A>
-static cudaError_t configure_rollout(int smem)
+static cudaError_t configure_rollout()
 {
     cudaError_t e = cudaSuccess;
-    MPPI_FOR_EACH_MODEL(if ((e = configure_rollout_s<A, kM>(smem)) != cudaSuccess) return e);
+    MPPI_FOR_EACH_MODEL(if ((e = configure_rollout_s<A, kM>()) != cudaSuccess) return e);
     return e;
 }
 
 cudaError_t configure_kernels(const LaunchCtx &c)
 {
     cudaError_t e = cudaSuccess;
-    const int avg_smem = (int)average_smem_bytes(c.rows);
-    if ((e = cudaFuncSetAttribute(average_kernel<true, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, avg_smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(average_kernel<true, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, avg_smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(average_kernel<false, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, avg_smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(average_kernel<false, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, avg_smem)) != cudaSuccess) return e;
-    const int fin = (int)(sizeof(float) * (size_t)c.rows);
-    if (fin > 48 * 1024) {
-        e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(xchg_sum_finalize_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(xchg_merge_finalize_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fin);
-        if (e != cudaSuccess) return e;
-    }
-    MPPI_DISPATCH_A(c.act_dim, e = configure_rollout_tma<kA>(c.horizon));
-    if (e != cudaSuccess) return e;
-    const int ro = (int)(sizeof(float) * (size_t)c.horizon * 16);
-    if (ro > 48 * 1024) {
-        MPPI_DISPATCH_A(c.act_dim, e = configure_rollout<kA>(ro));
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+    if ((e = opt_in(average_kernel<true, true>)) != cudaSuccess) return e;
+    if ((e = opt_in(average_kernel<true, false>)) != cudaSuccess) return e;
+    if ((e = opt_in(average_kernel<false, true>)) != cudaSuccess) return e;
+    if ((e = opt_in(average_kernel<false, false>)) != cudaSuccess) return e;
+    if ((e = opt_in(finalize_kernel)) != cudaSuccess) return e;
+    if ((e = opt_in(xchg_sum_finalize_kernel)) != cudaSuccess) return e;
+    if ((e = opt_in(xchg_merge_finalize_kernel)) != cudaSuccess) return e;
+    MPPI_DISPATCH_A(c.act_dim, e = configure_rollout<kA>());
+    return e;
+}
+
+// what this shape needs of every kernel it may launch, against the opt-in maximum; returns the
+// name of the first kernel that does not fit (nullptr: all fit)
+const char *check_smem_requirements(const LaunchCtx &c, size_t *need, size_t *have)
+{
+    *have = (size_t)(kSmemOptIn - kSmemStaticSlack);
+    struct { const char *name; size_t bytes; } req[] = {
+        {"average_kernel", average_smem_bytes(c.rows)},
+        {"finalize_kernel", sizeof(float) * (size_t)c.rows},
+        {"xchg_merge_finalize_kernel", xchg_merge_smem_bytes(c.rows)},
+        {"rollout_kernel", sizeof(float) * (size_t)c.horizon * 16},
+        {"rollout_tma_kernel",
+         c.act_dim == 1 ? rollout_tma_smem_bytes<1>(c.horizon, 256) :
+         c.act_dim == 2 ? rollout_tma_smem_bytes<2>(c.horizon, 256) :
+         c.act_dim == 3 ? rollout_tma_smem_bytes<3>(c.horizon, 256) :
+                          rollout_tma_smem_bytes<4>(c.horizon, 256)},
+    };
+    for (auto &r : req)
+        if (r.bytes > *have) { *need = r.bytes; return r.name; }
+    return nullptr;
 }
 
 cudaError_t launch_clear_ctl(const LaunchCtx &c, CtlDev *ctl)

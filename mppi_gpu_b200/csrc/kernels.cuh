@@ -3,6 +3,7 @@
 
 #include "common.cuh"
 #include "philox.cuh"
+#include "xchg.cuh"
 
 namespace mppi {
 
@@ -68,21 +69,19 @@ cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, cons
 cudaError_t launch_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
                             const ProblemDev *prob, CtlDev *ctl, float *next_act, unsigned flags);
 
-// K-shard exchange over NVLink peer mailboxes (MPPI_COMM_P2P); peer_mb[r] = mailbox of rank r
-// as mapped in this process (cudaIpcOpenMemHandle), peer_mb[rank] = the local one
-cudaError_t launch_xchg_min(const LaunchCtx &c, CtlDev *ctl, unsigned long long *const *peer_mb,
-                            int rank, int world);
+// K-shard exchange over NVLink peer mailboxes (MPPI_COMM_P2P) as kernels behind average_kernel;
+// xa from make_xchg_args (peer_mb[r] = mailbox of rank r as mapped in this process,
+// cudaIpcOpenMemHandle or a raw peer pointer; peer_mb[rank] = the local one)
+cudaError_t launch_xchg_min(const LaunchCtx &c, CtlDev *ctl, const XchgArgs &xa);
 cudaError_t launch_xchg_sum_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
                                      const ProblemDev *prob, CtlDev *ctl, float *next_act,
-                                     unsigned flags, unsigned long long *const *peer_mb, int rank,
-                                     int world);
+                                     unsigned flags, const XchgArgs &xa);
 
 // the single exchange of the online-softmax K-shard merge: every shard averaged relative to
 // its own minimum; push {key, acc}, rescale by exp(-(beta_r-beta)/lambda), sum, U update
 cudaError_t launch_xchg_merge_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
                                        const ProblemDev *prob, CtlDev *ctl, float *next_act,
-                                       unsigned flags, unsigned long long *const *peer_mb, int rank,
-                                       int world);
+                                       unsigned flags, const XchgArgs &xa);
 
 // layout conversion between the reference's [K][T*A] and the internal K-minor [T*A][k_pad]
 cudaError_t launch_to_internal(const LaunchCtx &c, const float *e_ref, float *eps);
@@ -102,17 +101,31 @@ cudaError_t launch_trajectories(const LaunchCtx &c, const float *eps, const floa
 bool step_kernel_supported(int T, int A, long long k_pad, int num_sms);
 size_t step_part_floats(const LaunchCtx &c);
 cudaError_t configure_step(const LaunchCtx &c);
-//       finalize = false (K-shards): the last CTA stops after writing the fixed-point
-//       accumulators (relative to the shard's own minimum); launch_xchg_merge_finalize follows.
+//       xa.world > 1 (K-shards): the last CTA also exchanges the merged sums (relative to the
+//       shard's own minimum) with the peers over NVLink before the U update (xchg.cuh).
 cudaError_t launch_step(const LaunchCtx &c, const CUtensorMap &tmap, float *eps, float *U,
-                        const ProblemDev *prob, float *S, CtlDev *ctl, float *part, long long *acc,
-                        float *U_prev, float *next_act, unsigned flags, bool finalize);
+                        const ProblemDev *prob, float *S, CtlDev *ctl, float *part,
+                        float *U_prev, float *next_act, unsigned flags, const XchgArgs &xa);
+XchgArgs make_xchg_args(unsigned long long *const *peer_mb, int rank, int world, int rows);
 constexpr int kStepTileK = 128, kStepTileR = 40;   // its TMA box
+
+// (1-5) the whole control step in one persistent kernel that keeps eps in SHARED MEMORY
+//       (tile.cu): per SM a tile of 64 samples is drawn by the generator warps, integrated by
+//       one packed-FP32x2 warp and folded into per-thread row sums; eps never reaches HBM.
+//       Same record / merge / finalize protocol as launch_step (part: step_part_floats()).
+bool tile_kernel_supported(int T, int A, long long k_pad, int num_sms);
+cudaError_t configure_tile(const LaunchCtx &c);
+//       xa.world > 1 (K-shards): the last CTA also runs the NVLink exchange (xchg.cuh).
+cudaError_t launch_tile(const LaunchCtx &c, float *U, const ProblemDev *prob, float *S, CtlDev *ctl,
+                        float *part, float *U_prev, float *next_act, unsigned flags,
+                        const XchgArgs &xa);
 
 // reset the control block (min key armed, step 0)
 cudaError_t launch_clear_ctl(const LaunchCtx &c, CtlDev *ctl);
 
-// one-time per-device opt-in to large dynamic shared memory for the shapes in c
+// opt-in of every kernel to the device's maximum of dynamic shared memory (per function and
+// device, never lowered), and the check of what the shape in c needs against that maximum
 cudaError_t configure_kernels(const LaunchCtx &c);
+const char *check_smem_requirements(const LaunchCtx &c, size_t *need, size_t *have);
 
 }  // namespace mppi

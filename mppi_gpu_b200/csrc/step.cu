@@ -46,6 +46,7 @@
 // rollout warps wait on nobody: the dependency graph has no cycle.
 #include "finalize.cuh"
 #include "kernels.cuh"
+#include "merge.cuh"
 #include "model.cuh"
 #include "philox.cuh"
 
@@ -86,7 +87,7 @@ __host__ __device__ inline StepSmemLayout step_smem_layout(int T, int A, long lo
 // rescale factors and at least eight records per bulk-copy pass
 __host__ __device__ inline size_t step_merge_bytes(int R, int grid)
 {
-    return (size_t)(R + 1) * 8 + (size_t)(R + grid) * 4 + 128 + (size_t)8 * ((R + 2 + 3) & ~3) * 4;
+    return merge_smem_bytes(R, grid);
 }
 
 #ifdef MPPI_STEP_TRACE
@@ -135,8 +136,8 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
             long long k_local, int T, const float *U,
             const ProblemDev *__restrict__ prob, float *__restrict__ S, CtlDev *__restrict__ ctl,
             unsigned long long k_offset, const __grid_constant__ SamplerParams sp,
-            float *__restrict__ part, long long *__restrict__ acc, FinalizeArgs fin,
-            int nstages, int do_finalize)
+            float *__restrict__ part, FinalizeArgs fin, int nstages,
+            const __grid_constant__ XchgArgs xa)
 {
     static_assert((NR + 1) % 4 == 0, "rollout warps + producer must fill whole warpgroups");
     constexpr int kThreads = (NR + kStConsumers + 1) * 32;
@@ -377,7 +378,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
 
     // ---- this CTA's record: {row sums [R], eta, ref}, all relative to ref; the stride is a
     //      multiple of four floats so that the merge reads float4 columns
-    const int rstride = (R + 2 + 3) & ~3;
+    const int rstride = record_stride(R);
     float *rec = part + (size_t)blockIdx.x * rstride;
     for (int rb = 2 * warp; rb < R; rb += 2 * (kEpiThreads / 32)) {      // two rows per warp pass
         const int r = rb + (lane >> 4);
@@ -399,77 +400,13 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
     }
     named_bar_sync(1, kEpiThreads);
     if (*s_last) {
-        // ---- merge the records in CTA order (deterministic), then part 5
-        __threadfence();
+        // ---- merge the records in CTA order (deterministic), then part 5 (merge.cuh).  The
+        //      ring, the row sums and the U staging are free now and serve as its scratch.
 #ifdef MPPI_STEP_TRACE
         if (threadIdx.x == 0) { g_step_trace_all[0][5] = gtimer(); g_step_trace_all[0][7] = blockIdx.x; }
 #endif
-        const float nil = prob->neg_inv_lambda;
-        const unsigned long long mk = *reinterpret_cast<volatile unsigned long long *>(&ctl->min_key);
-        const float beta = ordered_to_float((uint32_t)(mk >> 32));
-        const int nc = (int)gridDim.x;
-        // The ring, the row sums and the U staging are free now: the records are pulled into
-        // that region with ONE bulk copy per pass (as many records as fit) instead of strided
-        // L2 loads with a handful in flight per thread, and merged from shared memory.
-        constexpr int kMaxOut = 4;                                      // outputs per thread (R+1 <= 2048)
-        const size_t cap = L.scale;                                     // bytes of reusable shared memory
-        long long *s_acc = reinterpret_cast<long long *>(base);         // [R+1] merged, fixed point
-        float *s_unew = reinterpret_cast<float *>(s_acc + (R + 1));     // [R]
-        float *s_f = s_unew + R;                                        // [per pass]
-        const size_t rec_off = (((size_t)(R + 1) * 8 + (size_t)R * 4 + (size_t)nc * 4) + 127) & ~(size_t)127;
-        float *s_rec = reinterpret_cast<float *>(base + rec_off);       // [per pass][rstride]
-        const int per = (int)((cap - rec_off) / ((size_t)rstride * sizeof(float)));
-        uint64_t *mbar = reinterpret_cast<uint64_t *>(s_misc + 4);      // 8-byte aligned, unused so far
-        if (threadIdx.x == 0) {
-            mbar_init(mbar, 1);
-            fence_mbar_init();
-        }
-        double sum[kMaxOut];
-#pragma unroll
-        for (int o = 0; o < kMaxOut; ++o) sum[o] = 0.0;
-        uint32_t parity = 0;
-        for (int c0 = 0; c0 < nc; c0 += per, parity ^= 1) {
-            const int n = min(per, nc - c0);
-            named_bar_sync(1, kEpiThreads);                             // region free, barrier initialised
-            if (threadIdx.x == 0) {
-                fence_proxy_async_all();                                // generic accesses above -> async copy
-                const uint32_t bytes = (uint32_t)((size_t)n * rstride * sizeof(float));
-                mbar_arrive_expect_tx(mbar, bytes);
-                bulk_load_1d(s_rec, part + (size_t)c0 * rstride, bytes, mbar);
-            }
-            mbar_wait(mbar, parity);
-            for (int c = threadIdx.x; c < n; c += kEpiThreads)
-                s_f[c] = expf(__fmul_rn(nil, __fsub_rn(s_rec[(size_t)c * rstride + R + 1], beta)));   // +inf -> 0
-            named_bar_sync(1, kEpiThreads);
-#pragma unroll
-            for (int o = 0; o < kMaxOut; ++o) {
-                const int i = threadIdx.x + o * kEpiThreads;            // i == R: eta
-                if (i <= R) {
-                    double a = sum[o];
-                    for (int c = 0; c < n; ++c)                         // fixed order: CTA 0, 1, 2, ...
-                        a += (double)s_rec[(size_t)c * rstride + i] * (double)s_f[c];
-                    sum[o] = a;
-                }
-            }
-        }
-        named_bar_sync(1, kEpiThreads);
-#pragma unroll
-        for (int o = 0; o < kMaxOut; ++o) {
-            const int i = threadIdx.x + o * kEpiThreads;
-            if (i <= R) {
-                const long long q = __double2ll_rn(sum[o] * kAccScale);
-                if (do_finalize) s_acc[i] = q;                          // stays on chip
-                else             acc[i] = q;                            // K-shard: cross-GPU merge kernel next
-            }
-        }
-        if (!do_finalize) {
-            // the accumulators are relative to this shard's minimum, which stays in ctl->min_key
-            if (threadIdx.x == 0) ctl->done = 0;
-            return;
-        }
-        named_bar_sync(1, kEpiThreads);
-        finalize_body(s_acc, fin.U, fin.U_prev, prob, ctl, fin.next_act, fin.T, fin.A, fin.flags,
-                      s_unew, kEpiThreads, 1);
+        merge_records<4>(part, R, (int)gridDim.x, base, L.scale,
+                         reinterpret_cast<uint64_t *>(s_misc + 4), kEpiThreads, 1, prob, ctl, fin, xa);
 #ifdef MPPI_STEP_TRACE
         if (threadIdx.x == 0) { g_step_trace[0][203] = gtimer(); g_step_trace_all[0][6] = gtimer(); }
 #endif
@@ -541,13 +478,13 @@ StepGeom step_geom(int T, int A, long long k_pad, int num_sms)
 template <int A, class MODEL>
 cudaError_t launch_step_t(const LaunchCtx &c, const CUtensorMap &tmap, float *eps, float *U,
                           const ProblemDev *prob, float *S, CtlDev *ctl, float *part,
-                          long long *acc, const FinalizeArgs &fin, bool finalize)
+                          const FinalizeArgs &fin, const XchgArgs &xa)
 {
     const StepGeom g = step_geom(c.horizon, c.act_dim, c.k_pad, c.num_sms);
     if (g.nstages == 0) return cudaErrorInvalidConfiguration;
     step_kernel<A, MODEL, kStepNR><<<g.grid, (kStepNR + kStConsumers + 1) * 32, g.smem, c.stream>>>(
         tmap, eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U, prob, S, ctl,
-        (unsigned long long)c.k_offset, c.sampler, part, acc, fin, g.nstages, finalize ? 1 : 0);
+        (unsigned long long)c.k_offset, c.sampler, part, fin, g.nstages, xa);
     return cudaGetLastError();
 }
 
@@ -593,17 +530,17 @@ cudaError_t configure_step(const LaunchCtx &c)
 }
 
 cudaError_t launch_step(const LaunchCtx &c, const CUtensorMap &tmap, float *eps, float *U,
-                        const ProblemDev *prob, float *S, CtlDev *ctl, float *part, long long *acc,
-                        float *U_prev, float *next_act, unsigned flags, bool finalize)
+                        const ProblemDev *prob, float *S, CtlDev *ctl, float *part,
+                        float *U_prev, float *next_act, unsigned flags, const XchgArgs &xa)
 {
     FinalizeArgs fin{U, U_prev, next_act, c.horizon, c.act_dim, flags};
 #define MPPI_STEP_CASE(A_)                                                                       \
     case A_:                                                                                     \
         if (c.general_gains)                                                                     \
-            return c.strict ? launch_step_t<A_, Model<true, LinearAxis>>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize) \
-                            : launch_step_t<A_, Model<false, LinearAxis>>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize); \
-        return c.strict ? launch_step_t<A_, Model<true, DoubleIntegrator>>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize) \
-                        : launch_step_t<A_, Model<false, DoubleIntegrator>>(c, tmap, eps, U, prob, S, ctl, part, acc, fin, finalize)
+            return c.strict ? launch_step_t<A_, Model<true, LinearAxis>>(c, tmap, eps, U, prob, S, ctl, part, fin, xa) \
+                            : launch_step_t<A_, Model<false, LinearAxis>>(c, tmap, eps, U, prob, S, ctl, part, fin, xa); \
+        return c.strict ? launch_step_t<A_, Model<true, DoubleIntegrator>>(c, tmap, eps, U, prob, S, ctl, part, fin, xa) \
+                        : launch_step_t<A_, Model<false, DoubleIntegrator>>(c, tmap, eps, U, prob, S, ctl, part, fin, xa)
     switch (c.act_dim) {
         MPPI_STEP_CASE(1);
         MPPI_STEP_CASE(2);

@@ -46,6 +46,19 @@ def test_k_sharded_one_kernel_step():
 
 
 @pytest.mark.gpu
+def test_k_sharded_tile_kernel():
+    """K-shards running the on-chip tile kernel (MPPI_FLAG_TILE_KERNEL = 1024): the last CTA of
+    every shard's kernel runs the NVLink exchange itself -- one kernel per step on any number
+    of GPUs; three steps against the single-shard oracle, U bit-identical on every rank."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    r = _launch("p2p", min(n, 4), 29549, "1024")
+    assert r.returncode == 0 and "P2P_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("comm", ["nccl", "p2p"])
 def test_k_sharded_controller(comm):
     import torch

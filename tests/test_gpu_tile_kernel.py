@@ -1,0 +1,222 @@
+"""The on-chip control step (MPPI_FLAG_TILE_KERNEL, csrc/tile.cu): eps is drawn into shared
+memory, integrated and averaged there; it never reaches HBM.
+
+Same bars as tests/test_gpu_parity.py: the noise of the step is pulled through get_inf (here the
+controller re-draws it -- Philox is counter based) and injected into the oracle; rollout costs,
+beta and the argmin index are bit exact, eta / weights / U / next action within 1e-5 relative."""
+import numpy as np
+import pytest
+
+from conftest import REF_CFG, bits, make_inputs
+from test_gpu_parity import _assert_noise_close, _assert_parity, _close
+from test_gpu_step_kernel import _assert_against_float64
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mppi_gpu_b200 as m
+    return m
+
+
+def _flags(strict=False):
+    from mppi_gpu_b200 import capi
+    return capi.FLAG_TILE_KERNEL | (capi.FLAG_STRICT_ARITH if strict else 0)
+
+
+# shapes: one partial tile; ragged K (pad columns, all-padding tiles); every A; T*A not a multiple
+# of the 4-row generator unit; one pass / many passes; more tiles than CTAs
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("A,K,T,lam", [
+    (1, 5, 3, 1.0), (1, 1027, 37, 1.0), (2, 3000, 50, 1.0), (2, 2049, 23, 0.05),
+    (3, 5000, 60, 1.0), (3, 129, 7, 2.0), (4, 777, 41, 1.0), (4, 20000, 13, 0.3),
+    (3, 9473, 200, 1.0), (1, 300, 1, 1.0), (2, 64, 2, 1.0), (1, 40000, 250, 0.7),
+])
+def test_tile_kernel_matches_oracle(M, oracle, A, K, T, lam, strict):
+    cfg = REF_CFG[A]
+    x0, U, _ = make_inputs(K, T, A, seed=100 * A + T)
+    ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=7 + A, lam=lam, flags=_flags(strict))
+    assert ctl.flags() & M.capi.FLAG_TILE_KERNEL
+    ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+    p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], lam=lam,
+                            arith=oracle.ARITH_STRICT if strict else oracle.ARITH_FMA)
+    for step in range(3):
+        pre = ctl.get_u()
+        n0 = ctl.launch_count()
+        na = ctl.get_act()
+        assert ctl.launch_count() == n0 + 1      # one kernel per control step
+        inf = ctl.get_inf()
+        info = ctl.step_info()
+        assert info["step"] == step + 1
+        ref = oracle.step(p, x0, pre, inf["e"])
+        _assert_parity(na, inf, info, ref, K, T, A)
+        want = oracle.sample_eps(7 + A, step, 0, K, T, A, [0.025] * A)
+        _assert_noise_close(inf["e"], want, 0.025)
+    ctl.close()
+
+
+@pytest.mark.parametrize("A,K,T", [(3, 40000, 50), (2, 300000, 20), (1, 70001, 64)])
+def test_tile_kernel_equals_kernel_chain(M, A, K, T):
+    """Same seed, same inputs: the tile kernel and the kernel chains draw the same noise and
+    integrate it with the same arithmetic -- eps (re-drawn for the tap), costs, beta, argmin
+    identical; U equal to rounding (different summation order of the weighted average)."""
+    from mppi_gpu_b200 import capi
+    cfg = REF_CFG[A]
+    x0, U, _ = make_inputs(K, T, A, seed=31)
+    out = []
+    for fl in (capi.FLAG_FUSED_SAMPLING, capi.FLAG_TILE_KERNEL, capi.FLAG_STEP_KERNEL, 0):
+        ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=5, flags=fl)
+        ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+        ctl.get_act()
+        ctl.set_x(x0 * np.float32(0.5))
+        na = ctl.get_act()                      # second step: Philox step index 1
+        inf = ctl.get_inf(want_e=True)
+        out.append((na, inf, ctl.step_info()))
+        ctl.close()
+    (na0, i0, s0) = out[0]
+    for na, inf, info in out[1:]:
+        assert np.array_equal(bits(inf["e"]), bits(i0["e"]))
+        assert info["argmin"] == s0["argmin"]
+        assert _close(inf["nabla"], i0["nabla"], tol=1e-5)
+        assert _close(inf["u"], i0["u"], tol=1e-5) and _close(na, na0, tol=1e-5)
+
+
+def test_tile_kernel_several_tiles_per_cta(M, oracle):
+    """K large enough that every CTA runs many tiles: the running minimum is lowered, and the
+    row sums rescaled, many times."""
+    K, T, A = 700001, 12, 2
+    cfg = REF_CFG[A]
+    x0, U, _ = make_inputs(K, T, A, seed=5)
+    ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=11, lam=0.5, flags=_flags())
+    ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+    for _ in range(2):
+        pre = ctl.get_u()
+        na = ctl.get_act()
+        _assert_against_float64(oracle, ctl, na, pre, x0, K, T, A, 0.5, cfg, stride=1)
+    ctl.close()
+
+
+def test_tile_kernel_is_bitwise_reproducible(M):
+    """Units are pulled dynamically, but which warp draws a unit does not change its bits, and
+    tile -> CTA, row -> thread and the merge order are static: run to run the same bits."""
+    K, T, A = 400000, 25, 3
+    cfg = REF_CFG[A]
+    x0, U, _ = make_inputs(K, T, A, seed=8)
+    runs = []
+    for _ in range(3):
+        ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=2, flags=_flags())
+        ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+        acts = np.array([ctl.get_act() for _ in range(4)])
+        runs.append((acts, ctl.get_u(), ctl.step_info()["eta"]))
+        ctl.close()
+    for acts, u, eta in runs[1:]:
+        assert np.array_equal(bits(acts), bits(runs[0][0]))
+        assert np.array_equal(bits(u), bits(runs[0][1]))
+        assert bits(np.float32(eta)) == bits(np.float32(runs[0][2]))
+
+
+def test_tile_kernel_falls_back_for_injected_noise(M, oracle):
+    """Injected noise lives in HBM: the handle runs the kernel chain instead."""
+    K, T, A = 3000, 50, 2
+    cfg = REF_CFG[A]
+    x0, U, eps = make_inputs(K, T, A, seed=3)
+    ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, flags=_flags())
+    ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+    ctl.set_noise(eps)
+    na = ctl.get_act()
+    inf = ctl.get_inf()
+    info = ctl.step_info()
+    p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], arith=oracle.ARITH_FMA)
+    ref = oracle.step(p, x0, U, eps)
+    _assert_parity(na, inf, info, ref, K, T, A)
+    assert ctl.launch_count() == 2
+    # back to sampled noise: the tile kernel again, and the tap re-draws that step's noise
+    ctl.set_noise_mode(False)
+    pre = ctl.get_u()
+    na = ctl.get_act()
+    inf = ctl.get_inf()
+    ref = oracle.step(p, x0, pre, inf["e"])
+    _assert_parity(na, inf, ctl.step_info(), ref, K, T, A)
+    ctl.close()
+
+
+def test_tile_kernel_falls_back_when_tile_does_not_fit(M, oracle):
+    """T*A too large for a 64-sample tile in shared memory: the flag is accepted and the step
+    runs on the kernel chain (sample, rollout, average)."""
+    K, T, A = 2000, 250, 4                      # R = 1000 rows: 272 KB
+    cfg = REF_CFG[A]
+    x0, U, _ = make_inputs(K, T, A, seed=13)
+    ctl = M.PointMassModel(K, T, 0.05, 2 * A, A, seed=1, flags=_flags())
+    ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+    na = ctl.get_act()
+    inf = ctl.get_inf()
+    info = ctl.step_info()
+    assert ctl.launch_count() == 3
+    p = oracle.make_problem(K, T, A, 0.05, cfg["goal"], cfg["w"], arith=oracle.ARITH_FMA)
+    ref = oracle.step(p, x0, U, inf["e"])
+    _assert_parity(na, inf, info, ref, K, T, A)
+    ctl.close()
+
+
+def test_tile_kernel_trajectory_tap(M, oracle):
+    """get_inf(x): trajectories recomputed from the re-drawn noise and the pre-update U."""
+    K, T, A = 500, 30, 2
+    cfg = REF_CFG[A]
+    x0, U, _ = make_inputs(K, T, A, seed=21)
+    ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=9, flags=_flags())
+    ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+    ctl.get_act()
+    inf = ctl.get_inf(want_x=True)
+    p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], arith=oracle.ARITH_FMA)
+    ref = oracle.step(p, x0, U, inf["e"])
+    assert np.array_equal(bits(inf["cost"]), bits(ref["S"]))
+    assert np.array_equal(bits(inf["x"][:, 0, :]), bits(np.tile(x0, (K, 1))))
+    ctl.close()
+
+
+def test_tile_kernel_full_size_point_mass3d(M, oracle):
+    """BASELINE.json configs[2] (K=1e6, T=200, A=3) through the tile kernel: size-independent
+    properties from the taps, and the costs of every 997th sample bit exact against the oracle."""
+    K, T, A = 1000000, 200, 3
+    cfg = REF_CFG[A]
+    ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=3, flags=_flags())
+    x0 = np.zeros(2 * A, np.float32)
+    U = np.zeros((T, A), np.float32)
+    ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+    na = ctl.get_act()
+    _assert_against_float64(oracle, ctl, na, U, x0, K, T, A, 1.0, cfg, stride=997)
+    ctl.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_shapes_tile_kernel(M, oracle, seed):
+    """Random (K, T, A, lambda, sigma, arithmetic, model) per seed through the tile kernel."""
+    from mppi_gpu_b200 import capi
+    rs = np.random.RandomState(4000 + seed)
+    A = int(rs.randint(1, 5))
+    T = int(rs.randint(1, 160 // A))
+    K = int(rs.choice([rs.randint(1, 300), rs.randint(300, 5000), rs.randint(5000, 60000)]))
+    lam = float(rs.choice([0.05, 0.5, 1.0, 7.0]))
+    sigma = float(rs.choice([0.01, 0.025, 0.3]))
+    strict = bool(rs.randint(0, 2))
+    gains = None
+    if rs.randint(0, 2):
+        gains = (np.array([1.0, 0.1, rs.uniform(-0.05, 0.05), rs.uniform(0.85, 1.0)], np.float32),
+                 np.array([rs.uniform(0.0, 0.02), rs.uniform(0.05, 0.3)], np.float32))
+    cfg = REF_CFG[A]
+    x0, U, _ = make_inputs(K, T, A, seed=seed)
+    kw = dict(seed=seed, lam=lam, sigma=sigma)
+    if gains is not None:
+        kw.update(state_gain=gains[0], act_gain=gains[1])
+    p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], lam=lam, gains=gains,
+                            arith=oracle.ARITH_STRICT if strict else oracle.ARITH_FMA)
+    ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, flags=_flags(strict), **kw)
+    ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+    ctl.get_act()                                   # step 0
+    pre = ctl.get_u()
+    na = ctl.get_act()                              # step 1, from the updated U
+    inf, info = ctl.get_inf(), ctl.step_info()
+    ctl.close()
+    ref = oracle.step(p, x0, pre, inf["e"])
+    _assert_parity(na, inf, info, ref, K, T, A)

@@ -1,0 +1,13 @@
+set -x
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests/test_gpu_tile_kernel.py tests/test_gpu_hardening.py -x -q -m gpu > gpurun_out/r2_tile_tests2.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2_tile_tests2.log
+tail -15 gpurun_out/r2_tile_tests2.log
+rm -f gpurun_out/r2_tile_prof2.log
+for K in 1000000 125000; do
+  timeout 120 python tools/quick_prof.py -K $K -T 200 -A 3 --flags 1024 --steps 20 2>/dev/null | tail -1 >> gpurun_out/r2_tile_prof2.log
+done
+timeout 120 python tools/quick_prof.py -K 100000 -T 200 -A 2 --flags 1024 --steps 50 2>/dev/null | tail -1 >> gpurun_out/r2_tile_prof2.log
+timeout 120 python tools/quick_prof.py -K 10000 -T 200 -A 2 --flags 1024 --steps 50 2>/dev/null | tail -1 >> gpurun_out/r2_tile_prof2.log
+timeout 120 python tools/quick_prof.py -K 100000 -T 50 -A 2 --flags 1024 --steps 50 2>/dev/null | tail -1 >> gpurun_out/r2_tile_prof2.log
+timeout 120 python tools/quick_prof.py -K 100000 -T 50 -A 2 --flags 256 --steps 50 2>/dev/null | tail -1 >> gpurun_out/r2_tile_prof2.log
+cat gpurun_out/r2_tile_prof2.log
