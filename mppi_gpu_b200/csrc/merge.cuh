@@ -32,7 +32,7 @@ __host__ __device__ inline size_t merge_smem_bytes(int R, int grid)
 // sums are relative to this shard's own minimum (ctl->min_key); the same CTA exchanges them with
 // the peers over NVLink (xchg.cuh) before the U update -- compute and collective in one kernel.
 template <int kMaxOut>
-__device__ __forceinline__ void merge_records(const float *__restrict__ part, int R, int nc,
+__device__ __noinline__ void merge_records(const float *__restrict__ part, int R, int nc,
                                               uint8_t *region, size_t cap, uint64_t *mbar, int nthr,
                                               int bar_id, const ProblemDev *__restrict__ prob,
                                               CtlDev *ctl, const FinalizeArgs &fin,

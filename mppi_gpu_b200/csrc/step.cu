@@ -186,6 +186,11 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
     }
     __syncthreads();
 
+    // The CTA is launched with 96 registers per thread.  setmaxnreg.inc can only draw on what the
+    // CTA itself has handed back: the consumer warpgroup's 128 threads x (96 - 32) = 8192 registers
+    // are exactly the 512 threads x (112 - 96) the four other warpgroups ask for.  Any pair that
+    // frees less than it claims (e.g. 48 / 112) deadlocks the kernel in setmaxnreg.inc.
+    static_assert(128 * (96 - 32) == (NR + 1) * 32 * (112 - 96), "setmaxnreg: the pool must balance");
     if (warp <= NR) setmaxnreg_inc<112>();
     else            setmaxnreg_dec<32>();
 

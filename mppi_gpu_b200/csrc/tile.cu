@@ -109,7 +109,7 @@ tile_kernel(long long k_local, int T, const float *__restrict__ U,
             const ProblemDev *__restrict__ prob, float *__restrict__ S, CtlDev *__restrict__ ctl,
             unsigned long long k_offset, const __grid_constant__ SamplerParams sp,
             float *__restrict__ part, FinalizeArgs fin, long long ntiles,
-            const __grid_constant__ XchgArgs xa, int dbg_skip)
+            const __grid_constant__ XchgArgs xa)
 {
     constexpr int kThreads = (NG + 1) * 32;
     constexpr int kGenThreads = NG * 32;
@@ -254,7 +254,6 @@ tile_kernel(long long k_local, int T, const float *__restrict__ U,
                 }
             };
             int t = 0;
-            if (dbg_skip) { need(R); t = T; }           // development aid: generator-bound timing
 #pragma unroll 1
             for (; t + kTlBlockSteps <= T; t += kTlBlockSteps) {
                 need((t + kTlBlockSteps) * A);
@@ -342,7 +341,7 @@ cudaError_t launch_tile_t(const LaunchCtx &c, float *U, const ProblemDev *prob, 
     if (!g.ok) return cudaErrorInvalidConfiguration;
     tile_kernel<A, MODEL, kTileNG><<<g.grid, (kTileNG + 1) * 32, g.smem, c.stream>>>(
         (long long)c.k_local, c.horizon, U, prob, S, ctl, (unsigned long long)c.k_offset, c.sampler,
-        part, fin, g.ntiles, xa, getenv("MPPI_TILE_DEBUG_SKIP") ? 1 : 0);
+        part, fin, g.ntiles, xa);
     return cudaGetLastError();
 }
 
