@@ -216,13 +216,14 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
     CK(mark());
     if (split) CK(launch_weights(c, h->d_S, h->d_prob, h->d_ctl, h->d_wt, h->d_acc));
     CK(mark());
-    const bool merge_fin = !split && !multi(h);
+    // single shard, or peer-mailbox shards merging with one exchange: the last CTA of the
+    // averaging kernel finishes the step (exchange included) -- no kernel behind it
+    const bool merge_fin = !split && (!multi(h) || one_xchg);
     CK(launch_average(c, h->tmap, split ? h->d_wt : h->d_S, h->d_acc, !split, merge_fin, h->d_prob,
-                      h->d_ctl, h->d_U, h->d_Uprev, h->d_next, h->p.flags));
+                      h->d_ctl, h->d_U, h->d_Uprev, h->d_next, h->p.flags, xa));
     CK(mark());
     if (one_xchg) {
-        CK(launch_xchg_merge_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
-                                      h->p.flags, xa));
+        // nothing: exchanged and finalized inside the averaging kernel
     } else if (p2p(h)) {
         // exchange + integer sum + U update in one kernel over peer memory
         CK(launch_xchg_sum_finalize(c, h->d_acc, h->d_U, h->d_Uprev, h->d_prob, h->d_ctl, h->d_next,
@@ -247,7 +248,8 @@ int kernels_per_step(const mppi_handle *h, bool sample)
     int n = 2;                                  // rollout, average(+weights,+finalize)
     if (sample && !fused(h)) n += 1;            // sampling
     if (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) n += 1;      // separate weights kernel
-    if (p2p(h)) n += (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) ? 2 : 1;   // (xchg_min,) xchg+finalize
+    if (p2p(h)) n += (h->p.flags & MPPI_FLAG_SPLIT_KERNELS) ? 2 : 0;   // xchg_min, xchg_sum+finalize;
+                                                                       // else inside the average
     else if (multi(h) || (h->p.flags & MPPI_FLAG_SPLIT_KERNELS)) n += 1;   // finalize kernel
     return n;
 }
@@ -938,7 +940,7 @@ int mppi_step_wait(mppi_handle *h, float *next_act)
             const bool ran = h->prof_one_kernel ? (i == MPPI_K_AVERAGE)
                            : (i == MPPI_K_SAMPLE) ? (sample && !fused(h))
                            : (i == MPPI_K_COMM_MIN) ? (multi(h) && (!p2p(h) || split))
-                           : (i == MPPI_K_COMM_SUM) ? multi(h)
+                           : (i == MPPI_K_COMM_SUM) ? (multi(h) && (!p2p(h) || split))
                            : (i == MPPI_K_WEIGHTS) ? split
                            : (i == MPPI_K_FINALIZE) ? ((split || multi(h)) && !p2p(h)) : true;
             if (ran) { h->ms_sum[i] += ms; h->launches[i] += 1; }

@@ -455,12 +455,15 @@ size_t average_smem_bytes(int R)
 //            the slab's eta once (in the CTA that owns the slab's first tile).
 //            Otherwise src is the weights array written by weights_kernel.
 // MERGE_FIN: the last CTA to finish (ticket from an atomic counter) applies the U update
-//            (part 5) -- single-shard only; multi-shard runs the all-reduce in between.
+//            (part 5); with K-shards over NVLink peer memory (xa.world > 1) it first runs the
+//            single exchange of xchg.cuh in line -- the shard averaged relative to its own
+//            minimum.  NCCL shards run their all-reduces between the kernels instead.
 template <bool MERGE_W, bool MERGE_FIN>
 __global__ void __launch_bounds__(kAvgThreads, 1)
 average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__restrict__ src,
                long long *__restrict__ acc, int rows, int nslab, int nchunk, long long k_local,
-               const ProblemDev *__restrict__ prob, CtlDev *__restrict__ ctl, FinalizeArgs fin)
+               const ProblemDev *__restrict__ prob, CtlDev *__restrict__ ctl, FinalizeArgs fin,
+               const __grid_constant__ XchgArgs xa)
 {
     // declared aligned (TMA destinations need 128 B): no integer round-trip on the address, so
     // the accesses below stay shared-space LDS/STS instead of generic loads
@@ -616,8 +619,27 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
         __syncthreads();
         if (s_last) {
             __threadfence();
-            finalize_body(acc, fin.U, fin.U_prev, prob, ctl, fin.next_act, fin.T, fin.A, fin.flags,
-                          s_tile);             // the tile ring is free now: reuse it for U_new
+            if (xa.world > 1) {
+                // the tile ring is free now: [rows+1] int64 accumulators, the rescale factors, U_new
+                long long *s_acc = reinterpret_cast<long long *>(s_tile);
+                double *s_f = reinterpret_cast<double *>(s_acc + (rows + 1));
+                float *s_un = reinterpret_cast<float *>(s_f + kMaxWorld + 1);
+                const volatile long long *vacc = acc;      // other CTAs' atomics: read at L2
+                for (int i = threadIdx.x; i <= rows; i += blockDim.x) {
+                    s_acc[i] = vacc[i];
+                    acc[i] = 0;                            // re-armed for the next step
+                }
+                __syncthreads();
+                if (!xchg_merge_body(s_acc, rows, prob, ctl, xa, s_f, (int)blockDim.x, 0)) {
+                    if (threadIdx.x == 0) publish_comm_error(ctl, fin.next_act);
+                    return;
+                }
+                finalize_body(s_acc, fin.U, fin.U_prev, prob, ctl, fin.next_act, fin.T, fin.A,
+                              fin.flags, s_un);
+            } else {
+                finalize_body(acc, fin.U, fin.U_prev, prob, ctl, fin.next_act, fin.T, fin.A,
+                              fin.flags, s_tile);      // the tile ring is free now: reuse it for U_new
+            }
         }
     }
 }
@@ -643,9 +665,10 @@ finalize_kernel(long long *__restrict__ acc, float *__restrict__ U, float *__res
 }
 
 // =================================================================================
-// K-shard exchange over NVLink peer memory (MPPI_COMM_P2P) as kernels of their own, behind
-// average_kernel.  Protocol, double buffering and the single-exchange merge: xchg.cuh (the
-// one-kernel steps run the same code in their last CTA).  A bounded spin (about two seconds)
+// K-shard exchange over NVLink peer memory (MPPI_COMM_P2P) as kernels of their own: the
+// two-exchange flow of MPPI_FLAG_SPLIT_KERNELS (beta first, then the sums).  The default
+// single-exchange merge runs inside the last CTA of average_kernel / step_kernel / tile_kernel
+// (xchg.cuh, where the protocol and its double buffering are described).  A bounded spin (about two seconds)
 // turns a dead peer into an error code instead of a hang; a failed exchange leaves U untouched.
 // =================================================================================
 constexpr int kXchgThreads = 512;
@@ -719,37 +742,6 @@ xchg_sum_finalize_kernel(long long *__restrict__ acc, float *__restrict__ U,
     __threadfence();
     __syncthreads();
     finalize_body(acc, U, U_prev, prob, ctl, next_act, T, A, flags, s_u);
-}
-
-// (3a+5'') ONE exchange per step behind average_kernel: xchg_merge_body on the shard's
-// accumulators (relative to its own minimum), then the U update.  Shared memory:
-// [R+1] int64 accumulators, [R] floats U_new, [kMaxWorld+1] doubles.
-__global__ void __launch_bounds__(kXchgThreads)
-xchg_merge_finalize_kernel(long long *__restrict__ acc, float *__restrict__ U,
-                           float *__restrict__ U_prev, const ProblemDev *__restrict__ prob,
-                           CtlDev *__restrict__ ctl, float *__restrict__ next_act, int T, int A,
-                           unsigned flags, const __grid_constant__ XchgArgs xa)
-{
-    extern __shared__ __align__(16) uint8_t s_x[];
-    const int R = T * A;
-    long long *s_acc = reinterpret_cast<long long *>(s_x);
-    double *s_f = reinterpret_cast<double *>(s_acc + (R + 1));
-    float *s_u = reinterpret_cast<float *>(s_f + kMaxWorld + 1);
-    for (int i = threadIdx.x; i <= R; i += blockDim.x) {
-        s_acc[i] = acc[i];
-        acc[i] = 0;                                // the global accumulators are re-armed here
-    }
-    __syncthreads();
-    if (!xchg_merge_body(s_acc, R, prob, ctl, xa, s_f, (int)blockDim.x, 0)) {
-        if (threadIdx.x == 0) publish_comm_error(ctl, next_act);
-        return;
-    }
-    finalize_body(s_acc, U, U_prev, prob, ctl, next_act, T, A, flags, s_u);
-}
-
-size_t xchg_merge_smem_bytes(int R)
-{
-    return (size_t)(R + 1) * 8 + (size_t)(kMaxWorld + 1) * 8 + (size_t)R * 4;
 }
 
 // =================================================================================
@@ -990,7 +982,7 @@ cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev 
 cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *src,
                            long long *acc, bool merge_weights, bool merge_finalize,
                            const ProblemDev *prob, CtlDev *ctl, float *U, float *U_prev,
-                           float *next_act, unsigned flags)
+                           float *next_act, unsigned flags, const XchgArgs &xa)
 {
     const size_t smem = average_smem_bytes(c.rows);
     const int nslab = (int)(c.k_pad / kAvgTileK);
@@ -998,7 +990,7 @@ cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, cons
     FinalizeArgs fin{U, U_prev, next_act, c.horizon, c.act_dim, flags};
 #define MPPI_AVG_LAUNCH(MW, MF)                                                                  \
     average_kernel<MW, MF><<<c.avg_grid, kAvgThreads, smem, c.stream>>>(                         \
-        tmap_eps, src, acc, c.rows, nslab, nchunk, (long long)c.k_local, prob, ctl, fin)
+        tmap_eps, src, acc, c.rows, nslab, nchunk, (long long)c.k_local, prob, ctl, fin, xa)
     if (merge_weights && merge_finalize) MPPI_AVG_LAUNCH(true, true);
     else if (merge_weights)              MPPI_AVG_LAUNCH(true, false);
     else if (merge_finalize)             MPPI_AVG_LAUNCH(false, true);
@@ -1039,15 +1031,6 @@ cudaError_t launch_xchg_sum_finalize(const LaunchCtx &c, long long *acc, float *
     const size_t smem = sizeof(float) * (size_t)c.rows;
     xchg_sum_finalize_kernel<<<1, kXchgThreads, smem, c.stream>>>(acc, U, U_prev, prob, ctl, next_act,
                                                                   c.horizon, c.act_dim, flags, xa);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_xchg_merge_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
-                                       const ProblemDev *prob, CtlDev *ctl, float *next_act,
-                                       unsigned flags, const XchgArgs &xa)
-{
-    xchg_merge_finalize_kernel<<<1, kXchgThreads, xchg_merge_smem_bytes(c.rows), c.stream>>>(
-        acc, U, U_prev, prob, ctl, next_act, c.horizon, c.act_dim, flags, xa);
     return cudaGetLastError();
 }
 
@@ -1134,7 +1117,6 @@ cudaError_t configure_kernels(const LaunchCtx &c)
     if ((e = opt_in(average_kernel<false, false>)) != cudaSuccess) return e;
     if ((e = opt_in(finalize_kernel)) != cudaSuccess) return e;
     if ((e = opt_in(xchg_sum_finalize_kernel)) != cudaSuccess) return e;
-    if ((e = opt_in(xchg_merge_finalize_kernel)) != cudaSuccess) return e;
     MPPI_DISPATCH_A(c.act_dim, e = configure_rollout<kA>());
     return e;
 }
@@ -1147,7 +1129,6 @@ const char *check_smem_requirements(const LaunchCtx &c, size_t *need, size_t *ha
     struct { const char *name; size_t bytes; } req[] = {
         {"average_kernel", average_smem_bytes(c.rows)},
         {"finalize_kernel", sizeof(float) * (size_t)c.rows},
-        {"xchg_merge_finalize_kernel", xchg_merge_smem_bytes(c.rows)},
         {"rollout_kernel", sizeof(float) * (size_t)c.horizon * 16},
         {"rollout_tma_kernel",
          c.act_dim == 1 ? rollout_tma_smem_bytes<1>(c.horizon, 256) :

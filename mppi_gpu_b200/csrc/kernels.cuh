@@ -59,29 +59,25 @@ cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev 
 // (4) acc[r] += sum_{k in cta's tiles} wt[k] * eps[r][k]   (fixed point, r < R)
 //     merge_weights : src = S, the weights (3) are formed inside (acc[R] += eta as well);
 //                     otherwise src = wt from launch_weights
-//     merge_finalize: the last CTA also runs (5) -- single shard only
+//     merge_finalize: the last CTA also runs (5); with xa.world > 1 (K-shards over NVLink peer
+//                     memory) it runs the single exchange of xchg.cuh first, in line
 cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *src,
                            long long *acc, bool merge_weights, bool merge_finalize,
                            const ProblemDev *prob, CtlDev *ctl, float *U, float *U_prev,
-                           float *next_act, unsigned flags);
+                           float *next_act, unsigned flags, const XchgArgs &xa);
 
 // (5) U += acc[0..R-1]/acc[R]; shift, next_act, advance step, re-arm acc and min key
 cudaError_t launch_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
                             const ProblemDev *prob, CtlDev *ctl, float *next_act, unsigned flags);
 
-// K-shard exchange over NVLink peer mailboxes (MPPI_COMM_P2P) as kernels behind average_kernel;
+// K-shard exchange over NVLink peer mailboxes (MPPI_COMM_P2P) as kernels of their own (the
+// two-exchange flow of MPPI_FLAG_SPLIT_KERNELS; the single-exchange merge runs in line);
 // xa from make_xchg_args (peer_mb[r] = mailbox of rank r as mapped in this process,
 // cudaIpcOpenMemHandle or a raw peer pointer; peer_mb[rank] = the local one)
 cudaError_t launch_xchg_min(const LaunchCtx &c, CtlDev *ctl, const XchgArgs &xa);
 cudaError_t launch_xchg_sum_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
                                      const ProblemDev *prob, CtlDev *ctl, float *next_act,
                                      unsigned flags, const XchgArgs &xa);
-
-// the single exchange of the online-softmax K-shard merge: every shard averaged relative to
-// its own minimum; push {key, acc}, rescale by exp(-(beta_r-beta)/lambda), sum, U update
-cudaError_t launch_xchg_merge_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
-                                       const ProblemDev *prob, CtlDev *ctl, float *next_act,
-                                       unsigned flags, const XchgArgs &xa);
 
 // layout conversion between the reference's [K][T*A] and the internal K-minor [T*A][k_pad]
 cudaError_t launch_to_internal(const LaunchCtx &c, const float *e_ref, float *eps);

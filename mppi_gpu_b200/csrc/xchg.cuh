@@ -1,7 +1,7 @@
 // xchg.cuh -- the K-shard exchange over NVLink peer memory (MPPI_COMM_P2P), as device code that
-// the finalizing CTA of ANY chain runs in line: the last CTA of tile_kernel / step_kernel
-// (compute and collective in one kernel) or the single CTA of xchg_merge_finalize_kernel
-// behind average_kernel.
+// the finalizing CTA of ANY chain runs in line: the last CTA of tile_kernel / step_kernel or of
+// average_kernel -- compute and collective in one kernel, no exchange launch on the step's
+// critical path.
 //
 // Every rank owns a mailbox with one slot per sender and per parity of the step number; a
 // sender stores its contribution straight into every peer's mailbox (st.relaxed.sys over

@@ -71,7 +71,7 @@ def gloo_mode():
 
 
 def gloo_merge_mode():
-    """CPU mirror of xchg_merge_finalize_kernel (csrc/kernels.cu): shard-local softmax reference,
+    """CPU mirror of xchg_merge_body (csrc/xchg.cuh): shard-local softmax reference,
     all-gather of {key, fixed-point accumulators}, rescale, sum in rank order."""
     from mppi_gpu_b200 import capi
     dist.init_process_group("gloo")

@@ -134,8 +134,11 @@ def test_single_process_device_group(oracle):
     ctl.get_act()
     kt = ctl.kernel_times()
     ctl.set_profiling(False)
-    # peer-mailbox shards merge with ONE exchange (online softmax): no beta exchange
-    assert kt["comm_min"][1] == 0 and kt["comm_sum"][1] == 1 and kt["average"][1] == 1
+    # peer-mailbox shards merge with ONE exchange (online softmax): no beta exchange, and the
+    # exchange itself runs inside the last CTA of the averaging kernel -- no kernel of its own
+    assert kt["comm_min"][1] == 0 and kt["comm_sum"][1] == 0 and kt["average"][1] == 1
+    xt = ctl.exchange_times()
+    assert xt["push_us"] > 0 and xt["merge_us"] > 0
     single.close()
     ctl.close()
 
