@@ -316,6 +316,35 @@ def closed_loop_config(m, capi, local_rank, nsteps=1000):
             "rollout_steps_per_s_p50": K * T / (lat[len(lat) // 2] * 1e-3)}
 
 
+def reference_gpu_path_ms(K, T, A, dt, goal, w, nsteps=6):
+    """BASELINE.json configs[1] asks for 'single B200 vs the reference sm_70-style GPU path':
+    oracle/_ref/ref_gpu_run is the reference's own point_mass.cu + point_mass_gpu.cu + cost.cu +
+    mppi_utils.cu, unmodified, recompiled -O3 for sm_100 behind a replay of src/main.cu:311-371
+    (oracle/Makefile ref-gpu; built where /root/reference exists, travels as a binary).  It times
+    its own get_act with a host clock as main.cu:329-332 does.  Returns the median ms per
+    get_act after the first (None when the binary is not there)."""
+    import struct
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_run")
+    if not os.path.exists(exe):
+        return None
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(struct.pack("<4i", K, T, A, nsteps))
+            f.write(struct.pack("<f", dt))
+            for arr in (np.zeros(2 * A), np.zeros(T * A), goal, w):
+                f.write(np.asarray(arr, np.float32).tobytes())
+        try:
+            r = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=120)
+            if r.returncode != 0:
+                return None
+            raw = np.fromfile(fout, np.float32)
+        except Exception:
+            return None
+    return float(np.median(raw[-nsteps:][1:]))
+
+
 def small_config(m, capi, local_rank, name, nsteps=200):
     """BASELINE.json configs[1] (and [0]'s shape on the GPU): device time per step and the
     latency of set_x + get_act with host buffers."""
@@ -341,8 +370,17 @@ def small_config(m, capi, local_rank, name, nsteps=200):
     flags = ctl.flags()
     ctl.close()
     lat = sorted(1e3 * v for v in lat)
-    return {"ms_per_step": ms, "rollout_steps_per_s": K * T / (ms * 1e-3), "p50_ms": lat[len(lat) // 2],
-            "p99_ms": lat[int(0.99 * len(lat))], "flags": flags}
+    out = {"ms_per_step": ms, "rollout_steps_per_s": K * T / (ms * 1e-3), "p50_ms": lat[len(lat) // 2],
+           "p99_ms": lat[int(0.99 * len(lat))], "flags": flags}
+    if A == 2:      # the only action dim whose average is not defective in the reference
+        ref_ms = reference_gpu_path_ms(K, T, A, dt, goal, w)
+        if ref_ms:
+            out["reference_gpu_path"] = {
+                "what": "the reference's own GPU path recompiled for sm_100 (oracle/_ref/ref_gpu_run), "
+                        "same GPU, same shape, its own host clock around get_act",
+                "ms_per_get_act": ref_ms, "rollout_steps_per_s": K * T / (ref_ms * 1e-3),
+                "speedup_p50": ref_ms / lat[len(lat) // 2]}
+    return out
 
 
 # --------------------------------------------------------------------------------- ours

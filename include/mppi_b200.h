@@ -72,10 +72,13 @@ extern "C" {
                                                silently uses the kernel chain                */
 
 #define MPPI_FLAG_AUTO_CHAIN      (1u << 8)  /* let the library pick the kernel chain from the
-                                               shard size (thresholds measured on B200):
-                                               >= 4e5 samples: MPPI_FLAG_STEP_KERNEL (single
-                                               shard or MPPI_COMM_P2P), >= 1.2e5:
-                                               MPPI_FLAG_FUSED_SAMPLING, else the unfused
+                                               shard's work (measured on B200, every T and A):
+                                               the one-kernel step once its rollout warps run
+                                               >= 1.4 tiles each and a pass over eps is >= 350 MB
+                                               (single shard or MPPI_COMM_P2P); else
+                                               MPPI_FLAG_FUSED_SAMPLING while the fused kernel
+                                               keeps >= 1.55 warps per SM sub-partition (about
+                                               1.2e5 samples on 148 SMs); else the unfused
                                                chain with MPPI_FLAG_PIPELINED_SAMPLING.
                                                mppi_get_flags returns the choice.             */
 

@@ -300,6 +300,33 @@ int leave_pipeline(mppi_handle *h)
     return MPPI_OK;
 }
 
+// MPPI_FLAG_AUTO_CHAIN: the chain is chosen from the shard's WORK, not from K alone.  What
+// decides between the chains (tools/chain_sweep.py: T in {50,100,200} x A in {1..4} x K 1e3..1e6,
+// profiles/r02_chain_sweep.jsonl; the choice is within 5 % of the best chain on all of them,
+// tests/test_gpu_step_kernel.py::test_auto_chain_is_within_5_percent_of_the_best):
+//   tiles_per_warp  128-sample tiles per rollout warp of the one-kernel step (15 warps per SM).
+//                   The step kernel overlaps the average of finished tiles with the rollout of
+//                   the next ones; with less than ~1.4 tiles per warp there is nothing to
+//                   overlap and its merge tail (~19 us) is pure cost.
+//   eps_bytes       one pass over the shard's eps.  Below ~350 MB a step is so short (< ~0.12 ms)
+//                   that the same tail outweighs the overlap: the fused chain wins (T=50, A=2,
+//                   K=5e5: 115 vs 121 us).
+//   warps_per_sched resident warps per SM sub-partition of the fused sample+rollout kernel (one
+//                   warp integrates 128 samples serially over T).  Below ~1.6 the kernel costs one
+//                   warp's T-step chain whatever K is, and the unfused chain -- whose sampler is
+//                   parallel over (k, t, a) -- is faster; it then draws the next step's noise
+//                   during the plant's turn (MPPI_FLAG_PIPELINED_SAMPLING).
+// All three crossovers move with the SM count, none with T or A (both sides scale alike).
+uint32_t auto_chain(const LaunchCtx &c, bool can_step)
+{
+    const double tiles_per_warp = (double)c.k_pad / 128.0 / (15.0 * c.num_sms);
+    const double eps_bytes = 4.0 * (double)c.k_pad * c.rows;
+    const double warps_per_sched = (double)c.k_pad / 128.0 / (4.0 * c.num_sms);
+    if (can_step && tiles_per_warp >= 1.4 && eps_bytes >= 3.5e8) return MPPI_FLAG_STEP_KERNEL;
+    if (warps_per_sched >= 1.55) return MPPI_FLAG_FUSED_SAMPLING;
+    return MPPI_FLAG_PIPELINED_SAMPLING;
+}
+
 int upload_problem(mppi_handle *h)
 {
     CK(cudaMemcpyAsync(h->d_prob, &h->h_prob, sizeof(ProblemDev), cudaMemcpyHostToDevice, h->stream));
@@ -586,18 +613,9 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     }
     CKH(configure_kernels(c));
     if (p.flags & MPPI_FLAG_AUTO_CHAIN) {
-        // thresholds measured on B200 at T=200 (tools/quick_prof.py): the one-kernel step wins once
-        // every rollout warp runs more than ~1.7 tiles, the fused two-kernel chain down to ~1e5
         const bool can_step = (p.world_size == 1 || p.comm == MPPI_COMM_P2P) &&
                               step_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms);
-        if (!(p.flags & MPPI_FLAG_SPLIT_KERNELS)) {
-            if (c.k_local >= 400000 && can_step) h->p.flags |= MPPI_FLAG_STEP_KERNEL;
-            else if (c.k_local >= 120000)        h->p.flags |= MPPI_FLAG_FUSED_SAMPLING;
-            // the unfused chain of a closed loop draws the next step's noise during the plant's
-            // turn: get_act is 3-28 % shorter for any plant time (K=1e5: 103 -> 100 us with an
-            // instantaneous plant, 74 us once the plant takes 40 us)
-            else                                 h->p.flags |= MPPI_FLAG_PIPELINED_SAMPLING;
-        }
+        if (!(p.flags & MPPI_FLAG_SPLIT_KERNELS)) h->p.flags |= auto_chain(c, can_step);
         h->p.flags &= ~MPPI_FLAG_AUTO_CHAIN;
     }
     if ((h->p.flags & MPPI_FLAG_PIPELINED_SAMPLING) &&

@@ -620,10 +620,11 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
         if (s_last) {
             __threadfence();
             if (xa.world > 1) {
-                // the tile ring is free now: [rows+1] int64 accumulators, the rescale factors, U_new
+                // the tile ring is free now: [rows+1] int64 accumulators, the rescale factors and the
+                // shards' keys (xchg_merge_body), U_new
                 long long *s_acc = reinterpret_cast<long long *>(s_tile);
                 double *s_f = reinterpret_cast<double *>(s_acc + (rows + 1));
-                float *s_un = reinterpret_cast<float *>(s_f + kMaxWorld + 1);
+                float *s_un = reinterpret_cast<float *>(s_f + 2 * (kMaxWorld + 1));   // s_f, then the keys
                 const volatile long long *vacc = acc;      // other CTAs' atomics: read at L2
                 for (int i = threadIdx.x; i <= rows; i += blockDim.x) {
                     s_acc[i] = vacc[i];

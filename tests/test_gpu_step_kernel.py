@@ -169,17 +169,19 @@ def test_step_kernel_full_size_point_mass3d(M, oracle):
     ctl.close()
 
 
-def test_auto_chain_picks_by_shard_size(M):
-    """MPPI_FLAG_AUTO_CHAIN: the library resolves the kernel chain from the shard size and
-    reports its choice; whatever it picks draws the same noise and produces the same costs."""
+def test_auto_chain_picks_by_work(M):
+    """MPPI_FLAG_AUTO_CHAIN: the library resolves the kernel chain from the shard's work (tiles
+    per rollout warp, bytes of one eps pass, warps per sub-partition) and reports its choice;
+    whatever it picks draws the same noise and produces the same costs."""
     from mppi_gpu_b200 import capi
-    T, A = 10, 2
+    A = 2
     cfg = REF_CFG[A]
-    want = {50000: capi.FLAG_PIPELINED_SAMPLING, 150000: capi.FLAG_FUSED_SAMPLING,
-            450000: capi.FLAG_STEP_KERNEL}
-    for K, chain in want.items():
+    want = {(50000, 10): capi.FLAG_PIPELINED_SAMPLING, (150000, 10): capi.FLAG_FUSED_SAMPLING,
+            (450000, 10): capi.FLAG_FUSED_SAMPLING,     # enough tiles, but a 36 MB step is too short
+            (450000, 120): capi.FLAG_STEP_KERNEL}
+    for (K, T), chain in want.items():
         ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=4, flags=capi.FLAG_AUTO_CHAIN)
-        assert ctl.flags() == chain, (K, ctl.flags())
+        assert ctl.flags() == chain, (K, T, ctl.flags())
         ctl.memcpy_set_data(np.zeros(4), np.zeros((T, A)), cfg["goal"], cfg["w"])
         na = ctl.get_act()
         cost = ctl.get_inf(want_e=False)["cost"]
@@ -190,6 +192,46 @@ def test_auto_chain_picks_by_shard_size(M):
         assert np.array_equal(bits(ref.get_inf(want_e=False)["cost"]), bits(cost))
         assert _close(na, na0, tol=2e-6)
         ref.close()
+
+
+def _device_ms(M, K, T, A, flags, steps):
+    cfg = REF_CFG[A]
+    ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=1, flags=flags)
+    ctl.memcpy_set_data(np.zeros(2 * A), np.zeros((T, A)), cfg["goal"], cfg["w"])
+    for _ in range(5):
+        ctl.get_act()
+    best = None
+    for _ in range(3):                          # best of three regions: launch noise out
+        ctl.timer_start()
+        for _ in range(steps):
+            ctl.step_enqueue()
+        ms = ctl.timer_stop() / steps
+        ctl.step_wait()
+        best = ms if best is None else min(best, ms)
+    got = ctl.flags()
+    ctl.close()
+    return best, got
+
+
+@pytest.mark.parametrize("A,T,K", [
+    (3, 200, 30000), (3, 200, 125000), (3, 200, 500000), (2, 50, 100000), (2, 50, 500000),
+    (1, 200, 250000), (4, 100, 125000), (1, 50, 1000000), (4, 50, 400000),
+])
+def test_auto_chain_is_within_5_percent_of_the_best(M, A, T, K):
+    """The chain MPPI_FLAG_AUTO_CHAIN resolves to against the three chains timed on the same
+    shape (device time of graph-replayed steps).  The comparison is between chain families: the
+    latency option the auto chain adds to the unfused chain (pipelined sampling) is masked, it
+    trades back-to-back throughput for time after the state arrives."""
+    from mppi_gpu_b200 import capi
+    steps = 100 if K <= 150000 else 30
+    ms = {}
+    for name, fl in (("unfused", 0), ("fused", capi.FLAG_FUSED_SAMPLING), ("step", capi.FLAG_STEP_KERNEL)):
+        ms[name], _ = _device_ms(M, K, T, A, fl, steps)
+    _, chosen = _device_ms(M, K, T, A, capi.FLAG_AUTO_CHAIN, 5)
+    family = chosen & ~capi.FLAG_PIPELINED_SAMPLING
+    auto_ms, _ = _device_ms(M, K, T, A, family, steps)
+    best = min(ms.values())
+    assert auto_ms <= 1.05 * best + 1.5e-3, (chosen, auto_ms, ms)
 
 
 def test_step_kernel_falls_back_when_rows_do_not_fit(M, oracle):
