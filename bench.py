@@ -389,6 +389,7 @@ def run_ours(args, name, K, T, A, dt, goal, w):
     import mppi_gpu_b200 as m
     from mppi_gpu_b200 import capi
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")     # stdout carries the JSON line and nothing else
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

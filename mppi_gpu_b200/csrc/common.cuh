@@ -238,18 +238,14 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 #endif  // __CUDACC__
 
 // Peer mailbox of one rank: two buffers (parity of the step number) of one slot per sender;
-// slot s is written only by rank s (over NVLink for s != self).  Two layouts share a slot:
-//   single exchange (xchg.cuh): 2*(R+2) packets of 8 bytes {value half, sequence number} -- the
-//     packed key, then the R+1 accumulators, low half first; a packet is valid when it carries
-//     the step's sequence number, so the exchange needs no fence and no separate flag
-//   two exchanges (MPPI_FLAG_SPLIT_KERNELS):
-//     [0] key_seq  [1] key  [2] acc_seq  [3] reserved  [4 ...] acc[R+1]
+// slot s is written only by rank s (over NVLink for s != self).
+//   [0] seq (single exchange) / key_seq  [1] key  [2] acc_seq  [3] reserved  [4 ...] acc[R+1]
 constexpr int kMailboxHeaderWords = 4;
 constexpr int kMaxWorld = 16;
 constexpr int kMailboxBuffers = 2;
 inline size_t mailbox_slot_words(int rows)
 {
-    return (size_t)((2 * (rows + 2) + 15) / 16 * 16);                     // 128-byte multiple
+    return (size_t)((kMailboxHeaderWords + rows + 1 + 15) / 16 * 16);     // 128-byte multiple
 }
 
 }  // namespace mppi

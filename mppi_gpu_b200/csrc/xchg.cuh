@@ -5,11 +5,8 @@
 //
 // Every rank owns a mailbox with one slot per sender and per parity of the step number; a
 // sender stores its contribution straight into every peer's mailbox (st.relaxed.sys over
-// NVLink) as 8-byte packets that carry the step's sequence number beside the payload; the owner
-// polls its own memory until every packet shows that number.  One NVLink store latency per
-// exchange: no fence, no flag, no second round trip.  (The two-exchange flow of
-// MPPI_FLAG_SPLIT_KERNELS keeps data + fence + flag, compared with >=.)  Sequence = control
-// step + 1, never reset.
+// NVLink), fences, then publishes the sequence number (st.release.sys); the owner polls its
+// own memory (ld.acquire.sys).  Sequence = control step + 1, never reset, compared with >=.
 //
 // Why two buffers: a rank can enter exchange n+1 only after it has seen every peer's flag of
 // exchange n, and a peer raises that flag before it reads the others' data; so a fast rank's
@@ -38,8 +35,8 @@ struct XchgArgs {
     unsigned long long slot_words;
 };
 
-// %globaltimer stamps of the last exchange, CtlDev::t_xchg: [0] push begins, [1] own packets
-// are out, [2] every peer's key has arrived (the wait for the slowest rank), [3] merged
+// %globaltimer stamps of the last exchange, CtlDev::t_xchg: [0] push begins, [1] own data and
+// flags are out, [2] every peer's flag has arrived, [3] merged
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
     unsigned long long t;
@@ -75,34 +72,14 @@ __device__ __forceinline__ void publish_comm_error(CtlDev *ctl, float *next_act)
     st_release_sys_u64(reinterpret_cast<unsigned long long *>(next_act + kNextSeqOffset), step);
 }
 
-// One 8-byte packet of the single exchange: {32 bits of payload, 32 bits of sequence number}.
-// An aligned 8-byte store is single-copy atomic, also over NVLink, so a packet that shows the
-// step's sequence number carries the step's payload: no fence before a flag, no flag at all.
-// (The same idea as the low-latency protocol of NCCL.)
-__device__ __forceinline__ void put_packets(unsigned long long *pk, unsigned long long v, uint32_t seq32)
-{
-    const unsigned long long tag = (unsigned long long)seq32 << 32;
-    st_relaxed_sys_u64(pk + 0, tag | (v & 0xffffffffull));
-    st_relaxed_sys_u64(pk + 1, tag | (v >> 32));
-}
-// true when both halves carry seq32; *v is then the 64-bit payload
-__device__ __forceinline__ bool get_packets(const unsigned long long *pk, uint32_t seq32,
-                                            unsigned long long *v)
-{
-    const unsigned long long lo = ld_relaxed_sys_u64(pk + 0), hi = ld_relaxed_sys_u64(pk + 1);
-    *v = (lo & 0xffffffffull) | (hi << 32);
-    return (uint32_t)(lo >> 32) == seq32 && (uint32_t)(hi >> 32) == seq32;
-}
-
 // ONE exchange per step.  Every shard has averaged with ITS OWN minimum beta_r as the softmax
 // reference, so s_acc[0..R-1] = sum_k w~_k eps_k and s_acc[R] = eta_r are relative to beta_r
-// (ctl->min_key).  Each rank pushes {key_r, acc_r} to every peer as packets, takes the global
-// minimum key, rescales every shard's accumulators by exp(-(beta_r - beta)/lambda) and sums them
-// in rank order in double -- the same arithmetic on the same bits on every rank, so the
-// replicated U stays bit-identical.  On return (true) s_acc holds the merged sums and
-// ctl->min_key the global key.  Called by the threads [0, nthr) of one CTA; s_acc [R+1] and s_f
-// [2 * (kMaxWorld + 1)] (rescale factors, then the shards' keys) are shared memory.  Returns false (for every thread) when a peer did not
-// arrive within about two seconds.
+// (ctl->min_key).  Each rank pushes {key_r, acc_r} to every peer, takes the global minimum key,
+// rescales every shard's accumulators by exp(-(beta_r - beta)/lambda) and sums them in rank
+// order in double -- the same arithmetic on the same bits on every rank, so the replicated U
+// stays bit-identical.  On return (true) s_acc holds the merged sums and ctl->min_key the global
+// key.  Called by the threads [0, nthr) of one CTA; s_acc [R+1] and s_f [kMaxWorld + 1] are
+// shared memory.  Returns false (for every thread) when a peer did not arrive.
 __device__ __forceinline__ bool xchg_merge_body(long long *s_acc, int R,
                                                 const ProblemDev *__restrict__ prob, CtlDev *ctl,
                                                 const XchgArgs &xa, double *s_f, int nthr, int bar_id)
@@ -110,69 +87,61 @@ __device__ __forceinline__ bool xchg_merge_body(long long *s_acc, int R,
     const int rank = xa.rank, world = xa.world;
     const size_t sw = (size_t)xa.slot_words;
     const unsigned long long seq = ctl->step + 1;
-    const uint32_t seq32 = (uint32_t)seq;
     const int par = (int)(seq & 1ull);
     const unsigned long long mine = ctl->min_key;
     if (threadIdx.x == 0) ctl->t_xchg[0] = globaltimer_ns();
-    // ---- push: element 0 is the key, elements 1..R+1 the accumulators
     for (int r = 0; r < world; ++r) {
         unsigned long long *slot = mb_slot(xa.peers.mb[r], par, world, rank, sw);
-        for (int j = threadIdx.x; j <= R + 1; j += nthr)
-            put_packets(slot + 2 * j, j == 0 ? mine : (unsigned long long)s_acc[j - 1], seq32);
+        if (threadIdx.x == 0) st_relaxed_sys_u64(slot + 1, mine);
+        for (int i = threadIdx.x; i <= R; i += nthr)
+            st_relaxed_sys_u64(slot + kMailboxHeaderWords + i, (unsigned long long)s_acc[i]);
     }
-    if (threadIdx.x == 0) ctl->t_xchg[1] = globaltimer_ns();
-    // ---- every peer's key (this is where a slow rank is waited for)
-    unsigned long long *my = xa.peers.mb[rank] + (size_t)par * world * sw;      // local memory
-    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_f + kMaxWorld + 1);
+    __threadfence_system();
+    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nthr) : "memory");
     if (threadIdx.x < world) {
-        const unsigned long long *pk = my + (size_t)threadIdx.x * sw;
-        unsigned long long k = kMinKeyInit;
-        const long long t0 = clock64();
-        while (!get_packets(pk, seq32, &k)) {
-            if (clock64() - t0 > 4000000000ll) { atomicExch(&ctl->comm_error, 1u); break; }
-            __nanosleep(32);
-        }
-        s_key[threadIdx.x] = k;
+        st_release_sys_u64(mb_slot(xa.peers.mb[threadIdx.x], par, world, rank, sw) + 0, seq);
+        if (threadIdx.x == 0) ctl->t_xchg[1] = globaltimer_ns();
+        const unsigned long long *in = mb_slot(xa.peers.mb[rank], par, world, threadIdx.x, sw);
+        if (!wait_seq(in + 0, seq)) atomicExch(&ctl->comm_error, 1u);
     }
     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nthr) : "memory");
     if (*reinterpret_cast<volatile unsigned int *>(&ctl->comm_error)) return false;
+    unsigned long long *my = xa.peers.mb[rank] + (size_t)par * world * sw;      // local memory
     if (threadIdx.x == 0) {
         ctl->t_xchg[2] = globaltimer_ns();
+        unsigned long long keys[kMaxWorld];
         unsigned long long gkey = kMinKeyInit;
-        for (int r = 0; r < world; ++r) gkey = s_key[r] < gkey ? s_key[r] : gkey;
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            if (r < world) {
+                keys[r] = ld_relaxed_sys_u64(my + (size_t)r * sw + 1);
+                gkey = keys[r] < gkey ? keys[r] : gkey;
+            }
         const float beta = ordered_to_float((uint32_t)(gkey >> 32));
         const float nil = prob->neg_inv_lambda;
-        for (int r = 0; r < world; ++r) {
-            const float beta_r = ordered_to_float((uint32_t)(s_key[r] >> 32));
-            s_f[r] = s_key[r] == kMinKeyInit ? 0.0
-                                             : (double)expf(__fmul_rn(nil, __fsub_rn(beta_r, beta)));
-        }
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            if (r < world) {
+                const float beta_r = ordered_to_float((uint32_t)(keys[r] >> 32));
+                s_f[r] = keys[r] == kMinKeyInit ? 0.0
+                                                : (double)expf(__fmul_rn(nil, __fsub_rn(beta_r, beta)));
+            }
         ctl->min_key = gkey;                      // beta / argmin of the whole step
     }
     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nthr) : "memory");
-    // ---- the accumulators: all ranks' packets of an element are loaded together (independent
-    //      loads in flight), re-polled until complete, then summed in rank order
-    bool late = false;
     for (int i = threadIdx.x; i <= R; i += nthr) {
-        unsigned long long v[kMaxWorld];
-        const long long t0 = clock64();
-        for (;;) {
-            bool ok = true;
+        // all loads first (independent, in flight together), then the sum in rank order
+        long long v[kMaxWorld];
 #pragma unroll
-            for (int r = 0; r < kMaxWorld; ++r)
-                if (r < world) ok &= get_packets(my + (size_t)r * sw + 2 * (i + 1), seq32, &v[r]);
-            if (ok) break;
-            if (clock64() - t0 > 4000000000ll) { late = true; break; }
-        }
+        for (int r = 0; r < kMaxWorld; ++r)
+            v[r] = r < world ? (long long)ld_relaxed_sys_u64(my + (size_t)r * sw + kMailboxHeaderWords + i) : 0ll;
         double sum = 0.0;
 #pragma unroll
         for (int r = 0; r < kMaxWorld; ++r)
-            if (r < world) sum += (double)(long long)v[r] * s_f[r];
+            if (r < world) sum += (double)v[r] * s_f[r];
         s_acc[i] = __double2ll_rn(sum);
     }
-    if (late) atomicExch(&ctl->comm_error, 1u);
     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nthr) : "memory");
-    if (*reinterpret_cast<volatile unsigned int *>(&ctl->comm_error)) return false;
     if (threadIdx.x == 0) ctl->t_xchg[3] = globaltimer_ns();
     return true;
 }
