@@ -652,7 +652,7 @@ def run_ours(args, name, K, T, A, dt, goal, w):
             coll["p2p"] = {
                 "kind": "ONE exchange per step over NVLink peer mailboxes (direct P2P stores + flags), "
                         + ("inside the last CTA of the step's kernel" if one_kernel else
-                           "in a single-CTA kernel behind average_kernel")
+                           "inside the last CTA of average_kernel")
                         + ": every shard averages relative to its own minimum, the exchange rescales "
                           "by exp(-(beta_r-beta)/lambda), sums in rank order and applies the U update",
                 "push_us": med(xt["push_us"]), "wait_slowest_us": med(xt["wait_slowest_us"]),

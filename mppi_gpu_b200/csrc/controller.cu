@@ -168,6 +168,31 @@ int encode_tmap(mppi_handle *h, CUtensorMap *out, int box_cols, int box_rows, fl
     return MPPI_OK;
 }
 
+int encode_eps_tmaps(mppi_handle *h)
+{
+    int rc;
+    if ((rc = encode_tmap(h, &h->tmap, kAvgTileK, kAvgTileR)) != MPPI_OK) return rc;
+    if ((rc = encode_tmap(h, &h->tmap_st, kStepTileK, kStepTileR)) != MPPI_OK) return rc;
+    return encode_tmap(h, &h->tmap_ro, h->ctx.rollout_tma_width, rollout_tma_rows(h->p.act_dim));
+}
+
+// The eps buffer of a tile-kernel handle, on first need (see mppi_create).
+int ensure_eps(mppi_handle *h)
+{
+    if (h->d_eps) return MPPI_OK;
+    const size_t eps_bytes = sizeof(float) * (size_t)h->R * (size_t)h->ctx.k_pad;
+    cudaError_t e = cudaMalloc(&h->d_eps, eps_bytes);
+    if (e != cudaSuccess) {
+        h->d_eps = nullptr;
+        cudaGetLastError();
+        return fail(MPPI_ERR_CUDA, "the eps buffer (%zu bytes: K_local x T x A floats) cannot be allocated: %s; "
+                    "a tile-kernel handle steps without it, but injected noise and the eps / trajectory "
+                    "taps need it", eps_bytes, cudaGetErrorString(e));
+    }
+    CK(cudaMemsetAsync(h->d_eps, 0, eps_bytes, h->stream));
+    return encode_eps_tmaps(h);
+}
+
 // Enqueue the kernel chain of one control step on h->stream.  evs (optional) receives one
 // event before the first kernel and one after each stage (profiling mode).
 int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
@@ -570,7 +595,14 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     }
     c.stream = h->stream;
     const size_t eps_bytes = sizeof(float) * (size_t)h->R * (size_t)c.k_pad;
-    CKH(cudaMalloc(&h->d_eps, eps_bytes));
+    // A handle that runs the on-chip tile kernel never stores eps: its buffer (4*K*T*A bytes --
+    // 240 GB at K=1e8, T=200, A=3, more than the GPU has) is only allocated if something asks
+    // for the noise in memory (injected noise, the eps / trajectory taps, mppi_sample_only):
+    // ensure_eps().  Every other chain needs it from the first step.
+    h->tile_ok = (p.flags & MPPI_FLAG_TILE_KERNEL) && !(p.flags & MPPI_FLAG_SPLIT_KERNELS) &&
+                 !(p.flags & MPPI_FLAG_INJECTED_NOISE) && (p.world_size == 1 || p.comm == MPPI_COMM_P2P) &&
+                 tile_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms);
+    if (!h->tile_ok) CKH(cudaMalloc(&h->d_eps, eps_bytes));
     CKH(cudaMalloc(&h->d_S, sizeof(float) * (size_t)c.k_pad));
     if (p.flags & MPPI_FLAG_SPLIT_KERNELS)     // the materialised weights of the split chain only
         CKH(cudaMalloc(&h->d_wt, sizeof(float) * (size_t)c.k_pad));
@@ -592,7 +624,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     CKH(cudaHostGetDevicePointer(&h->d_next, h->h_next, 0));
     // eps zeroed like the reference's cudaMemset(_e, 0) (src/point_mass.cu:69): keeps the
     // pad columns finite and defines injected-noise mode before the first mppi_set_noise.
-    CKH(cudaMemsetAsync(h->d_eps, 0, eps_bytes, h->stream));
+    if (h->d_eps) CKH(cudaMemsetAsync(h->d_eps, 0, eps_bytes, h->stream));
     CKH(cudaMemsetAsync(h->d_S, 0, sizeof(float) * (size_t)c.k_pad, h->stream));
     if (h->d_wt) CKH(cudaMemsetAsync(h->d_wt, 0, sizeof(float) * (size_t)c.k_pad, h->stream));
     CKH(cudaMemsetAsync(h->d_acc, 0, sizeof(long long) * ((size_t)h->R + 1), h->stream));
@@ -632,8 +664,6 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     }
     h->step_ok = (h->p.flags & MPPI_FLAG_STEP_KERNEL) &&
                  step_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms);
-    h->tile_ok = (h->p.flags & MPPI_FLAG_TILE_KERNEL) &&
-                 tile_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms);
     if (h->step_ok) CKH(configure_step(c));
     if (h->tile_ok) CKH(configure_tile(c));
     if (h->step_ok || h->tile_ok) {
@@ -664,9 +694,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
         pd.max_act[a] = p.max_act[a];
     }
     if ((rc = upload_problem(h)) != MPPI_OK) { mppi_destroy(h); return rc; }
-    if ((rc = encode_tmap(h, &h->tmap, kAvgTileK, kAvgTileR)) != MPPI_OK) { mppi_destroy(h); return rc; }
-    if ((rc = encode_tmap(h, &h->tmap_st, kStepTileK, kStepTileR)) != MPPI_OK) { mppi_destroy(h); return rc; }
-    if ((rc = encode_tmap(h, &h->tmap_ro, c.rollout_tma_width, rollout_tma_rows(p.act_dim))) != MPPI_OK) { mppi_destroy(h); return rc; }
+    if (h->d_eps && (rc = encode_eps_tmaps(h)) != MPPI_OK) { mppi_destroy(h); return rc; }
     if (h->d_eps_alt) {
         if ((rc = encode_tmap(h, &h->tmap_alt, kAvgTileK, kAvgTileR, h->d_eps_alt)) != MPPI_OK) { mppi_destroy(h); return rc; }
         if ((rc = encode_tmap(h, &h->tmap_ro_alt, c.rollout_tma_width, rollout_tma_rows(p.act_dim), h->d_eps_alt)) != MPPI_OK) { mppi_destroy(h); return rc; }
@@ -856,6 +884,7 @@ int mppi_step_enqueue(mppi_handle *h)
         return fail(MPPI_ERR_STATE, "mppi_step before mppi_comm_p2p_connect");
     const bool sample = !h->injected;
     const int which = sample ? 0 : 1;
+    if (!tile_step(h, sample) && (rc = ensure_eps(h)) != MPPI_OK) return rc;
     if (pipelined(h, sample)) {
         // step n: the chain reads d_eps, which the sampler filled after step n-1 had published
         // its action -- during the plant's turn; the sampler of step n+1 is queued behind this
@@ -1059,6 +1088,7 @@ int mppi_get_info(mppi_handle *h, float *x, float *u, float *e, float *cost, flo
                         cudaGetErrorString(e__));                                         \
         }                                                                                 \
     } while (0)
+    if ((e || x) && (rc = ensure_eps(h)) != MPPI_OK) return rc;
     if ((e || x) && h->eps_on_chip) {
         // the last step kept its noise in shared memory: draw it again (counter based: same bits)
         CKS(launch_sample(c, h->d_eps, h->d_ctl, true, h->eps_step));
@@ -1120,6 +1150,7 @@ int mppi_set_noise(mppi_handle *h, const float *e)
     const LaunchCtx &c = h->ctx;
     const size_t n = (size_t)c.k_local * h->R;
     if ((rc = leave_pipeline(h)) != MPPI_OK) return rc;   // d_eps may be receiving noise drawn ahead
+    if ((rc = ensure_eps(h)) != MPPI_OK) return rc;
     h->eps_last = h->d_eps;
     h->eps_on_chip = false;
     float *scratch = nullptr;
@@ -1144,6 +1175,7 @@ int mppi_sample_only(mppi_handle *h, uint64_t step)
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
     if ((rc = leave_pipeline(h)) != MPPI_OK) return rc;
+    if ((rc = ensure_eps(h)) != MPPI_OK) return rc;
     h->eps_last = h->d_eps;                              // what get_inf returns next
     h->eps_on_chip = false;
     CK(launch_sample(h->ctx, h->d_eps, h->d_ctl, true, step));
