@@ -694,6 +694,32 @@ def run_ours(args, name, K, T, A, dt, goal, w):
                 "value": K * T / (max_over_ranks(ms_n) * 1e-3)}
         out["collectives_ms"] = coll
         out["details"]["comm"] = args.comm
+        if not args.no_weak_probe and name == DEFAULT_WORKLOAD:
+            # BASELINE.json fixes K globally (strong scaling: the shards shrink with N and fall below
+            # the size at which the kernels run at their large-K efficiency).  Beside it, the same
+            # ranks with the single-GPU shard size each (K = N x 1e6): what N GPUs sustain when the
+            # problem is allowed to grow.  Extra information, not the headline value.
+            if ctl is not None:
+                ctl.close()
+                ctl = None
+            from mppi_gpu_b200.torch_dist import sharded_controller
+            cw = sharded_controller(K * world, T, dt, 2 * A, A, comm=args.comm, device=local_rank, seed=0,
+                                    flags=capi.FLAG_AUTO_CHAIN)
+            cw.memcpy_set_data(x0, np.zeros((T, A), np.float32), goal, w)
+            for _ in range(5):
+                cw.get_act()
+            barrier()
+            cw.timer_start()
+            for _ in range(args.steps):
+                cw.step_enqueue()
+            ms_w = cw.timer_stop() / args.steps
+            cw.step_wait()
+            barrier()
+            ms_w = max_over_ranks(ms_w)
+            out["details"]["weak_scaling_probe"] = {
+                "K_global": K * world, "k_local": cw.k_local, "flags": cw.flags(), "ms_per_step": ms_w,
+                "value": K * world * T / (ms_w * 1e-3), "unit": UNIT}
+            cw.close()
 
     # ---- BASELINE.json configs[1] and [4] through the same API (N=1 only; < 2 s)
     if rank == 0 and world == 1 and name == DEFAULT_WORKLOAD and not args.no_extra_configs:
@@ -745,6 +771,7 @@ def main():
     ap.add_argument("--no-other-chains", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true")
     ap.add_argument("--no-nccl-leg", action="store_true")
+    ap.add_argument("--no-weak-probe", action="store_true")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="K-shard exchange for --gpus > 1: NVLink peer mailboxes or NCCL")
     args = ap.parse_args()
