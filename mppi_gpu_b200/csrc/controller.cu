@@ -325,30 +325,49 @@ int leave_pipeline(mppi_handle *h)
     return MPPI_OK;
 }
 
-// MPPI_FLAG_AUTO_CHAIN: the chain is chosen from the shard's WORK, not from K alone.  What
-// decides between the chains (tools/chain_sweep.py: T in {50,100,200} x A in {1..4} x K 1e3..1e6,
-// profiles/r02_chain_sweep.jsonl; the choice is within 5 % of the best chain on all of them,
-// tests/test_gpu_step_kernel.py::test_auto_chain_is_within_5_percent_of_the_best):
-//   tiles_per_warp  128-sample tiles per rollout warp of the one-kernel step (15 warps per SM).
-//                   The step kernel overlaps the average of finished tiles with the rollout of
-//                   the next ones; with less than ~1.4 tiles per warp there is nothing to
-//                   overlap and its merge tail (~19 us) is pure cost.
-//   eps_bytes       one pass over the shard's eps.  Below ~350 MB a step is so short (< ~0.12 ms)
-//                   that the same tail outweighs the overlap: the fused chain wins (T=50, A=2,
-//                   K=5e5: 115 vs 121 us).
-//   warps_per_sched resident warps per SM sub-partition of the fused sample+rollout kernel (one
-//                   warp integrates 128 samples serially over T).  Below ~1.6 the kernel costs one
-//                   warp's T-step chain whatever K is, and the unfused chain -- whose sampler is
-//                   parallel over (k, t, a) -- is faster; it then draws the next step's noise
-//                   during the plant's turn (MPPI_FLAG_PIPELINED_SAMPLING).
-// All three crossovers move with the SM count, none with T or A (both sides scale alike).
+// MPPI_FLAG_AUTO_CHAIN: the chain is chosen from an estimate of what each of the three costs on
+// this shard (microseconds per control step), not from K alone.  The rollouts are bound by the
+// FMA pipe of an SM sub-partition (Philox IMAD.WIDE and the packed FP32 dynamics share it,
+// tools/ubench/pipes.cu), so what a sample+rollout pass costs is the number of 128-sample warps
+// on the FULLEST sub-partition times the horizon -- a step function of the shard size -- while
+// the eps passes are HBM streams with a fixed start-up cost.  Constants fitted on one B200
+// (tools/chain_sweep.py: 7 (A, T) shapes x 16 shard sizes from 3e3 to 1e6, among them the 3-, 5-, 6-
+// and 7-GPU shards of K = 1e6, profiles/r02_chain_sweep_v2.jsonl: the chosen family is within 3.6 %
+// of the fastest on all 112); the choice is held to 5 % of the best chain by
+// tests/test_gpu_step_kernel.py::test_auto_chain_is_within_5_percent_of_the_best.
+//   fused    rollout: warps on the fullest sub-partition (rollout_warps_per_sched(); one warp
+//            alone costs about as much as two: 1.9) x R x 0.086 us; average eps_bytes / 6.4 TB/s;
+//            13.5 us of launches and tails; 7 us more once eps is twice the L2 (the average then
+//            competes with the write-back of what the rollout left dirty)
+//   unfused  sampler eps_bytes / 5.6 TB/s, rollout eps_bytes / 6.0 TB/s, average eps_bytes / 6.4 TB/s;
+//            16.5 + 0.02 R us of launches, tails and one slab's serial chain
+//   both     the streaming parts cost 3 % less than the sum of the kernels when replayed as a graph
+//   step     15 rollout warps per SM, one tile each per round: max(list/4, ceil(min(list,15)/4))
+//            x R x 0.0925 us, then what the consumers still have to read when the last rollout
+//            ends -- one round of tiles at ~44 GB/s per SM -- and ~48 us of start-up, merge and
+//            U update
+struct ChainCost { double fused, unfused, step; };
+ChainCost chain_cost(const LaunchCtx &c)
+{
+    const double R = c.rows, sms = c.num_sms;
+    const double eps_bytes = 4.0 * (double)c.k_pad * R;
+    const double warps = (double)((c.k_pad / 4 + 31) / 32);              // 128-sample warps
+    ChainCost k;
+    k.fused = 0.97 * (fmax(rollout_warps_per_sched(c.k_pad, c.num_sms), 1.9) * R * 0.086 +
+                      eps_bytes / 6.4e6) + 13.5 + (eps_bytes > 2.5e8 ? 7.0 : 0.0);
+    k.unfused = 0.97 * (eps_bytes / 5.6e6 + eps_bytes / 6.0e6 + eps_bytes / 6.4e6) + 16.5 + 0.02 * R;
+    const double list = ceil(warps / sms);                               // tiles of the fullest CTA
+    const double per_sched = fmax(warps / sms / 4.0, ceil(fmin(list, 15.0) / 4.0));
+    const double drain = fmin(warps / sms, 15.0) * R * 512.0 / 44.0e3;
+    k.step = per_sched * R * 0.0925 + drain + 48.0;
+    return k;
+}
+
 uint32_t auto_chain(const LaunchCtx &c, bool can_step)
 {
-    const double tiles_per_warp = (double)c.k_pad / 128.0 / (15.0 * c.num_sms);
-    const double eps_bytes = 4.0 * (double)c.k_pad * c.rows;
-    const double warps_per_sched = (double)c.k_pad / 128.0 / (4.0 * c.num_sms);
-    if (can_step && tiles_per_warp >= 1.4 && eps_bytes >= 3.5e8) return MPPI_FLAG_STEP_KERNEL;
-    if (warps_per_sched >= 1.55) return MPPI_FLAG_FUSED_SAMPLING;
+    const ChainCost k = chain_cost(c);
+    if (can_step && k.step < k.fused && k.step < k.unfused) return MPPI_FLAG_STEP_KERNEL;
+    if (k.fused <= k.unfused) return MPPI_FLAG_FUSED_SAMPLING;
     return MPPI_FLAG_PIPELINED_SAMPLING;
 }
 

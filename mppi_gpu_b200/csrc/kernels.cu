@@ -879,6 +879,39 @@ __global__ void clear_ctl_kernel(CtlDev *ctl)
         { using kM = Model<false, LinearAxis>; __VA_ARGS__; }                            \
     } while (0)
 
+// CTA size of rollout_kernel.  A small shard is a handful of warps per SM, and what its rollout
+// costs is the number of warps on the fullest SM sub-partition (the kernel is bound by the FMA
+// pipe, one per sub-partition): with 256-thread CTAs a shard of 163 CTAs puts two of them -- four
+// warps per sub-partition -- on 15 SMs and one on the others (K = 166 667: 0.279 ms per step against
+// 0.227 with 128-thread CTAs).  Take the largest CTA that reaches the smallest such count.
+// k_pad4: samples at four per thread (the fused kernel; SPT < 4 launches scale it).
+static void rollout_shape(long long k_pad4, int num_sms, int *threads, long long *per_sched)
+{
+    const long long warps = (k_pad4 / 4 + 31) / 32;
+    *per_sched = -1;
+    *threads = 256;
+    for (int t = 256; t >= 64; t >>= 1) {
+        const long long w = t / 32, ctas = (warps + w - 1) / w;
+        const long long per_sm = (ctas + num_sms - 1) / num_sms;
+        const long long ps = (per_sm * w + 3) / 4;
+        if (*per_sched < 0 || ps < *per_sched) { *per_sched = ps; *threads = t; }
+    }
+}
+int rollout_block_threads(long long k_pad4, int num_sms)
+{
+    int t; long long ps;
+    rollout_shape(k_pad4, num_sms, &t, &ps);
+    return t;
+}
+double rollout_warps_per_sched(long long k_pad, int num_sms)
+{
+    int t; long long ps;
+    rollout_shape(k_pad, num_sms, &t, &ps);
+    // far beyond one resident wave (16 warps per SM) the waves average out
+    const double avg = 1.05 * (double)((k_pad / 4 + 31) / 32) / (4.0 * num_sms);
+    return ps > 8 ? (avg > 8.0 ? avg : 8.0) : (double)ps;
+}
+
 cudaError_t launch_sample(const LaunchCtx &c, float *eps, const CtlDev *ctl,
                           bool use_step_override, unsigned long long step_override)
 {
@@ -900,10 +933,12 @@ static cudaError_t launch_rollout_t(const LaunchCtx &c, float *eps, const float 
                                     const ProblemDev *prob, float *S, CtlDev *ctl)
 {
     const size_t groups = (size_t)c.k_pad / SPT;
-    const unsigned grid = (unsigned)((groups + 255) / 256);
+    // CTA size: see rollout_block_threads()
+    const int threads = rollout_block_threads(c.k_pad / SPT * 4, c.num_sms);
+    const unsigned grid = (unsigned)((groups + threads - 1) / threads);
     const size_t smem = sizeof(float) * (size_t)c.horizon *
                         (SPT >= 2 ? UStage2<A>::kStride : UStage<A>::kStride);
-    rollout_kernel<A, MODEL, FUSED, SPT><<<grid, 256, smem, c.stream>>>(
+    rollout_kernel<A, MODEL, FUSED, SPT><<<grid, threads, smem, c.stream>>>(
         eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U, prob, S, ctl,
         (unsigned long long)c.k_offset, c.sampler);
     return cudaGetLastError();

@@ -46,6 +46,12 @@ cudaError_t launch_sample(const LaunchCtx &c, float *eps, const CtlDev *ctl,
 cudaError_t launch_rollout(const LaunchCtx &c, float *eps, const float *U, const ProblemDev *prob,
                            float *S, CtlDev *ctl, bool fused_sampling);
 
+// CTA size of rollout_kernel for a shard of k_pad4 samples at four per thread, and the number of
+// its 128-sample warps on the fullest SM sub-partition (what the fused pass costs, in units of
+// one warp's horizon)
+int rollout_block_threads(long long k_pad4, int num_sms);
+double rollout_warps_per_sched(long long k_pad, int num_sms);
+
 // (2b) the same rollout fed by TMA tiles (tensor map with box {rollout_tma_width,
 //      rollout_tma_rows(A)})
 cudaError_t launch_rollout_tma(const LaunchCtx &c, const CUtensorMap &tmap, const float *U,

@@ -176,7 +176,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
     for (int i = threadIdx.x; i < nchunk * kStTileR * 16; i += kThreads) s_part[i] = 0.0f;
     for (int i = threadIdx.x; i < (int)list_len; i += kThreads) s_done[i] = 0u;
     if (threadIdx.x == 0) {
-        *s_next = 0u;
+        *s_next = (unsigned int)NR;
         for (int s = 0; s < nstages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -190,8 +190,13 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
     // CTA itself has handed back: the consumer warpgroup's 128 threads x (96 - 32) = 8192 registers
     // are exactly the 512 threads x (112 - 96) the four other warpgroups ask for.  Any pair that
     // frees less than it claims (e.g. 48 / 112) deadlocks the kernel in setmaxnreg.inc.
-    static_assert(128 * (96 - 32) == (NR + 1) * 32 * (112 - 96), "setmaxnreg: the pool must balance");
-    if (warp <= NR) setmaxnreg_inc<112>();
+    // NR = 15: 640 threads launched with 96, rollout + producer grow to 112; NR = 11: 512 threads
+    // launched with 128, rollout + producer grow to 160 (fewer warps, each with room to keep several
+    // Philox streams in flight)
+    constexpr uint32_t kRegLaunch = NR == 15 ? 96 : 128, kRegRoll = NR == 15 ? 112 : 160;
+    static_assert(128 * (kRegLaunch - 32) == (NR + 1) * 32 * (kRegRoll - kRegLaunch),
+                  "setmaxnreg: the pool must balance");
+    if (warp <= NR) setmaxnreg_inc<kRegRoll>();
     else            setmaxnreg_dec<32>();
 
     if (warp < NR) {
@@ -200,10 +205,20 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
         m2.load(prob);
         const unsigned long long step = ctl->step;
         unsigned long long key = kMinKeyInit;
+        // First tile: list entry `warp` -- warp w sits on sub-partition w % 4, so a short list (a
+        // small shard: fewer tiles than rollout warps) spreads evenly over the four sub-partitions
+        // instead of landing wherever the race for the counter puts it (measured at 125k samples:
+        // rollouts done after 117 us on CTAs that happened to balance, 165 us on those with three or
+        // four tiles on one sub-partition).  Later tiles are pulled from the counter, which starts
+        // behind the first round.
+        bool first = true;
         for (;;) {
-            unsigned int li = 0;
-            if (lane == 0) li = atomicAdd(s_next, 1u);
-            li = __shfl_sync(0xffffffffu, li, 0);
+            unsigned int li = (unsigned int)warp;
+            if (!first) {
+                if (lane == 0) li = atomicAdd(s_next, 1u);
+                li = __shfl_sync(0xffffffffu, li, 0);
+            }
+            first = false;
             if ((long long)li >= list_len) break;
             const long long tile = (long long)li * gridDim.x + blockIdx.x;
             const size_t g = (size_t)tile * 32 + lane;                 // this lane's Philox quad
@@ -442,7 +457,10 @@ extern "C" int mppi_debug_read_step_trace_li(unsigned long long *out)
 // launch wrappers
 // =================================================================================
 namespace {
-constexpr int kStepNR = 15;   // rollout warps per CTA (+ 1 producer = 4 warpgroups)
+#ifndef MPPI_STEP_NR
+#define MPPI_STEP_NR 15
+#endif
+constexpr int kStepNR = MPPI_STEP_NR;   // rollout warps per CTA (+ 1 producer = whole warpgroups)
 constexpr size_t kStepSmemMax = 227 * 1024;
 
 struct StepGeom {

@@ -170,15 +170,18 @@ def test_step_kernel_full_size_point_mass3d(M, oracle):
 
 
 def test_auto_chain_picks_by_work(M):
-    """MPPI_FLAG_AUTO_CHAIN: the library resolves the kernel chain from the shard's work (tiles
-    per rollout warp, bytes of one eps pass, warps per sub-partition) and reports its choice;
-    whatever it picks draws the same noise and produces the same costs."""
+    """MPPI_FLAG_AUTO_CHAIN: the library resolves the kernel chain from an estimate of what each
+    chain costs on the shard (warps on the fullest SM sub-partition, bytes of one eps pass, tiles
+    per rollout round; controller.cu: chain_cost) and reports its choice; whatever it picks draws
+    the same noise and produces the same costs.  The four shapes are clear cases of the sweep
+    profiles/r02_chain_sweep_v2.jsonl."""
     from mppi_gpu_b200 import capi
     A = 2
     cfg = REF_CFG[A]
-    want = {(50000, 10): capi.FLAG_PIPELINED_SAMPLING, (150000, 10): capi.FLAG_FUSED_SAMPLING,
-            (450000, 10): capi.FLAG_FUSED_SAMPLING,     # enough tiles, but a 36 MB step is too short
-            (450000, 120): capi.FLAG_STEP_KERNEL}
+    want = {(30000, 200): capi.FLAG_PIPELINED_SAMPLING,   # one warp per sub-partition: the unfused chain
+            (150000, 200): capi.FLAG_FUSED_SAMPLING,
+            (450000, 10): capi.FLAG_FUSED_SAMPLING,       # enough tiles, but a 36 MB step is too short
+            (700000, 120): capi.FLAG_STEP_KERNEL}
     for (K, T), chain in want.items():
         ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=4, flags=capi.FLAG_AUTO_CHAIN)
         assert ctl.flags() == chain, (K, T, ctl.flags())
@@ -216,6 +219,9 @@ def _device_ms(M, K, T, A, flags, steps):
 @pytest.mark.parametrize("A,T,K", [
     (3, 200, 30000), (3, 200, 125000), (3, 200, 500000), (2, 50, 100000), (2, 50, 500000),
     (1, 200, 250000), (4, 100, 125000), (1, 50, 1000000), (4, 50, 400000),
+    # shard sizes between the powers of two (the 6- and 3-GPU shards of K = 1e6): the rollout cost
+    # is a step function of the warps on the fullest SM sub-partition
+    (3, 200, 166667), (3, 200, 333334), (2, 120, 450000),
 ])
 def test_auto_chain_is_within_5_percent_of_the_best(M, A, T, K):
     """The chain MPPI_FLAG_AUTO_CHAIN resolves to against the three chains timed on the same

@@ -14,7 +14,7 @@ OUT = os.path.join(ROOT, "tools", "_build", os.environ.get("MPPI_TRACE_LIB", "li
 if not os.path.exists(OUT):
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
                            "-Xcompiler", "-fPIC", "-DMPPI_STEP_TRACE", "-shared", "-o", OUT,
-                           SRC + "/kernels.cu", SRC + "/step.cu", SRC + "/controller.cu",
+                           SRC + "/kernels.cu", SRC + "/step.cu", SRC + "/tile.cu", SRC + "/controller.cu",
                            SRC + "/comm.cpp", "-ldl"])
 from mppi_gpu_b200 import capi
 capi.LIB_PATH = OUT
