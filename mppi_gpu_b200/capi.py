@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmppi_b200.so")
+# MPPI_B200_LIB: development aid (A/B builds of the library under tools/_build)
+LIB_PATH = os.environ.get("MPPI_B200_LIB") or os.path.join(HERE, "libmppi_b200.so")
 
 MAX_ACT = 4
 COMM_ID_BYTES = 128

@@ -45,8 +45,11 @@ inline SamplerParams make_sampler_params(unsigned long long seed, const float *s
 #ifdef __CUDACC__
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const SamplerParams &sp)
 {
+#ifndef MPPI_PHILOX_ROUNDS
+#define MPPI_PHILOX_ROUNDS 10
+#endif
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < MPPI_PHILOX_ROUNDS; ++i) {
         const uint32_t hi0 = __umulhi(kPhiloxM0, c.x), lo0 = kPhiloxM0 * c.x;
         const uint32_t hi1 = __umulhi(kPhiloxM1, c.z), lo1 = kPhiloxM1 * c.z;
         c = make_uint4(hi1 ^ c.y ^ sp.k0[i], lo1, hi0 ^ c.w ^ sp.k1[i], lo0);
