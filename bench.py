@@ -35,6 +35,7 @@ Printed JSON line (rank 0):
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -563,12 +564,29 @@ def run_ours(args, name, K, T, A, dt, goal, w):
         except Exception:
             roofline["issue"] = None
     eps_bytes = 4.0 * k_local * T * A
+    # The sampling work is bound by the FMA pipe of the SM sub-partitions, not by HBM
+    # (tools/ubench/pipes.cu): per 128-sample warp and time step, A Philox calls of
+    # 16.33 IMAD.WIDE (4 pipe cycles each; 20 per call less the loop-invariant first rounds) + 12
+    # scalar FP, and for the rollout 24A+4 packed FP32x2 operations (2 cycles each).
+    sm_clk = ((clk or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+    n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    warps = math.ceil(k_local / 128.0)
+
+    def fma_pipe(ms, rollout, sampling):
+        cyc = warps * T * ((16.33 * 4 + 12) * A * (1 if sampling else 0) + (48.0 * A + 8) * (1 if rollout else 0))
+        return {"algorithmic_cycles_per_subpartition": cyc / (4 * n_sm),
+                "frac": cyc / (4 * n_sm) / (ms * 1e-3 * sm_clk)}
+
     per_kernel = {}
     for kname_, ms in kernels.items():
         d = {"ms": ms}
         if kname_ in ("sample", "rollout"):
             d["hbm_gbs"] = eps_bytes / (ms * 1e-3) / 1e9
             d["hbm_frac"] = d["hbm_gbs"] / peak
+        if kname_ == "sample":
+            d["fma_pipe"] = fma_pipe(ms, False, True)
+        if kname_ == "rollout" and (flags & capi.FLAG_FUSED_SAMPLING):
+            d["fma_pipe"] = fma_pipe(ms, True, True)
         per_kernel[kname_] = d
 
     chain = ("one kernel, eps on chip: generator warps -> shared-memory tile -> integrator warp -> "
@@ -644,6 +662,11 @@ def run_ours(args, name, K, T, A, dt, goal, w):
                                  "hbm_frac": eps_bytes / (v * 1e-3) / 1e9 / peak}
                                 if (k in ("sample", "rollout", "average") and not one) else {"ms": v})
                             for k, v in kt4.items()}}
+            if not one:
+                if "sample" in kt4:
+                    others[cname]["kernels"]["sample"]["fma_pipe"] = fma_pipe(kt4["sample"], False, True)
+                if "rollout" in kt4 and (cflags & capi.FLAG_FUSED_SAMPLING):
+                    others[cname]["kernels"]["rollout"]["fma_pipe"] = fma_pipe(kt4["rollout"], True, True)
         out["other_chains"] = others
     if world > 1:
         med = lambda v: statistics.median(v) if v else None

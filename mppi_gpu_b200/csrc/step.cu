@@ -211,15 +211,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
         // rollouts done after 117 us on CTAs that happened to balance, 165 us on those with three or
         // four tiles on one sub-partition).  Later tiles are pulled from the counter, which starts
         // behind the first round.
-        bool first = true;
-        for (;;) {
-            unsigned int li = (unsigned int)warp;
-            if (!first) {
-                if (lane == 0) li = atomicAdd(s_next, 1u);
-                li = __shfl_sync(0xffffffffu, li, 0);
-            }
-            first = false;
-            if ((long long)li >= list_len) break;
+        for (unsigned int li = (unsigned int)warp; (long long)li < list_len;) {
             const long long tile = (long long)li * gridDim.x + blockIdx.x;
             const size_t g = (size_t)tile * 32 + lane;                 // this lane's Philox quad
             f2 x2[2][2 * A], c2[2];
@@ -275,7 +267,9 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
             if (lane == 0) {
                 st_release_cta_shared_u32(&s_done[li], 1u);
                 STEP_TRACE_LI(0, li);
+                li = atomicAdd(s_next, 1u);
             }
+            li = __shfl_sync(0xffffffffu, li, 0);
         }
         key = warp_min_u64(key);
         if (lane == 0 && key != kMinKeyInit) atomicMin(&ctl->min_key, key);
