@@ -2,10 +2,11 @@
 //
 //   mppi_main -c <config.yaml> [-t traj.csv] [-s step_prefix] [--plant ideal|mjcf] [--steps N] [--samples K]
 //             [--horizon T] [--honour-config] [--seed S] [--devices 0,1,..] [--verify-config] [--quiet]
-//             [--model ideal|mjcf] [--plant-us N] [--flags BITS [--exact-flags]]
+//             [--model ideal|mjcf] [--plant-us N] [--flags BITS [--exact-flags]] [--terminal-w w0,w1,..]
 //
 // --plant-us N makes the plant's turn take N microseconds of host time (the reference steps
-// MuJoCo there); --flags adds MPPI_FLAG_* bits to the default MPPI_FLAG_AUTO_CHAIN.
+// MuJoCo there); --flags adds MPPI_FLAG_* bits to the default MPPI_FLAG_AUTO_CHAIN;
+// --terminal-w gives the final state of every rollout cost weights of its own (state_dim values).
 //
 // --model mjcf gives the controller the dynamics of the MJCF body instead of the reference's
 // double integrator (MPPI_MODEL_LINEAR_AXIS: the damped, geared point mass of envs/*.xml
@@ -112,6 +113,7 @@ int main(int argc, char **argv)
     long plant_us = 0;             // emulated compute time of the plant's step (busy wait)
     unsigned extra_flags = 0;      // MPPI_FLAG_* bits on top of the default (auto chain)
     bool exact_flags = false;
+    std::vector<float> terminal_w;
     std::vector<int> devices;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -131,6 +133,16 @@ int main(int argc, char **argv)
         else if (a == "--plant-us") plant_us = std::stol(next());
         else if (a == "--flags") extra_flags = (unsigned)std::stoul(next(), nullptr, 0);
         else if (a == "--exact-flags") exact_flags = true;   // --flags replaces the default
+        else if (a == "--terminal-w") {
+            std::string list = next();
+            size_t pos = 0;
+            while (pos <= list.size()) {
+                size_t c = list.find(',', pos);
+                if (c == std::string::npos) c = list.size();
+                if (c > pos) terminal_w.push_back(std::stof(list.substr(pos, c - pos)));
+                pos = c + 1;
+            }
+        }
         else if (a == "--devices") {           // e.g. --devices 0,1,2,3 : K sharded over GPUs
             std::string list = next();
             size_t pos = 0;
@@ -195,6 +207,13 @@ int main(int argc, char **argv)
 
     env.get_x(init_state.data());
     model->memcpy_set_data(init_state.data(), init_actions.data(), cfg.goal.data(), cfg.cost_w.data());
+    if (!terminal_w.empty()) {
+        if ((int)terminal_w.size() != state_dim) {
+            std::cerr << "--terminal-w needs " << state_dim << " values" << std::endl;
+            return 2;
+        }
+        model->set_terminal_weights(terminal_w.data());
+    }
     x.push_back(init_state);
 
     std::vector<double> lat_ms;

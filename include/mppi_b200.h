@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MPPI_ABI_VERSION 2
+#define MPPI_ABI_VERSION 3
 #define MPPI_MAX_ACT 4            /* supported action dims: 1..4 (state dim = 2A) */
 #define MPPI_COMM_ID_BYTES 128
 
@@ -201,6 +201,13 @@ int mppi_destroy(mppi_handle *h);
  * goal [S], cost weights w [S]. */
 int mppi_set_problem(mppi_handle *h, const float *x0, const float *u, const float *goal,
                      const float *w);
+
+/* Terminal weights: the final state x[T] is charged by a SECOND Cost object with weights
+ * w_final[state_dim] (Cost::final_cost, src/cost.cu:57-64, unchanged).  The reference uses one
+ * object for the stage and the final cost (src/point_mass_gpu.cu:107,116) although its Cost class
+ * takes the weights as an argument (include/cost.hpp:8-14); that remains the default, and NULL
+ * returns to it.  Sticky across mppi_set_problem.  No reference counterpart. */
+int mppi_set_terminal_weights(mppi_handle *h, const float *w_final);
 
 /* == set_x(x) (src/point_mass.cu:482-486): new initial state for the next step */
 int mppi_set_state(mppi_handle *h, const float *x);

@@ -100,6 +100,22 @@ public:
         check(mppi_set_problem(_h, x, u, goal, w), __LINE__);
     }
 
+    // not in the reference: the final state charged by a second Cost object (Cost::final_cost with
+    // w_final [state_dim]); nullptr returns to the reference's single object
+    void set_terminal_weights(const float *w_final)
+    {
+        check(mppi_set_terminal_weights(_h, w_final), __LINE__);
+    }
+
+    // not in the reference (README: "decouple x into q and q_dot"): the state as positions and
+    // velocities; x = [q, q_dot] (src/point_mass_gpu.cu:97-106)
+    void set_q(const float *q, const float *q_dot)
+    {
+        float x[2 * MPPI_MAX_ACT];
+        for (int i = 0; i < _act_dim; ++i) { x[i] = q[i]; x[i + _act_dim] = q_dot[i]; }
+        set_x(x);
+    }
+
     // reference: copies x [K,(T+1),S] and e [K,T,A] (src/point_mass.cu:230-234)
     void memcpy_get_data(float *x_all, float *e)
     {

@@ -41,7 +41,8 @@ K_SAMPLE, K_ROLLOUT, K_COMM_MIN, K_WEIGHTS, K_AVERAGE, K_COMM_SUM, K_FINALIZE, K
 
 # every symbol include/mppi_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "mppi_params_default", "mppi_create", "mppi_create_multi", "mppi_destroy", "mppi_set_problem", "mppi_set_state",
+    "mppi_params_default", "mppi_create", "mppi_create_multi", "mppi_destroy", "mppi_set_problem",
+    "mppi_set_terminal_weights", "mppi_set_state",
     "mppi_step", "mppi_step_enqueue", "mppi_step_wait", "mppi_get_u", "mppi_set_u",
     "mppi_get_info", "mppi_get_flags", "mppi_get_step_info", "mppi_set_noise", "mppi_set_noise_mode",
     "mppi_sample_only", "mppi_shard_range", "mppi_local_samples", "mppi_timer_start", "mppi_timer_stop",
@@ -114,6 +115,7 @@ def load():
     L.mppi_create_multi.argtypes = [C.POINTER(MppiParams), C.POINTER(C.c_int), C.c_int, C.POINTER(H)]
     L.mppi_destroy.argtypes = [H]
     L.mppi_set_problem.argtypes = [H, fp, fp, fp, fp]
+    L.mppi_set_terminal_weights.argtypes = [H, fp]
     L.mppi_set_state.argtypes = [H, fp]
     L.mppi_step.argtypes = [H, fp]
     L.mppi_step_enqueue.argtypes = [H]
@@ -142,7 +144,7 @@ def load():
         fn = getattr(L, name)
         if name not in ("mppi_last_error", "mppi_kernel_name"):
             fn.restype = C.c_int
-    if L.mppi_abi_version() != 2:
+    if L.mppi_abi_version() != 3:
         raise ImportError("libmppi_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -71,10 +71,27 @@ class PointMassModel:
         capi.check(self._lib.mppi_set_problem(self._h, x.ctypes.data, u.ctypes.data,
                                               goal.ctypes.data, w.ctypes.data))
 
+    def set_terminal_weights(self, w_final):
+        """The final state gets a Cost object of its own (Cost::final_cost with w_final); None:
+        back to the reference's single object.  No reference counterpart."""
+        if w_final is None:
+            capi.check(self._lib.mppi_set_terminal_weights(self._h, None))
+            return
+        wf = capi.f32(w_final)
+        assert wf.size == self.S
+        capi.check(self._lib.mppi_set_terminal_weights(self._h, wf.ctypes.data))
+
     def set_x(self, x):
         x = capi.f32(x)
         assert x.size == self.S
         capi.check(self._lib.mppi_set_state(self._h, x.ctypes.data))
+
+    def set_q(self, q, q_dot):
+        """The state as positions and velocities (README: "decouple x into q and q_dot"); the
+        state vector is [q, q_dot] (src/point_mass_gpu.cu:97-106: x[i], x[i + S/2])."""
+        q, q_dot = capi.f32(q), capi.f32(q_dot)
+        assert q.size == self.A and q_dot.size == self.A
+        self.set_x(np.concatenate([q, q_dot]))
 
     def get_act(self, next_act=None):
         out = np.zeros(self.A, np.float32) if next_act is None else next_act

@@ -30,6 +30,8 @@ struct ProblemDev {
     float b[2];            // action gain {dt*dt/2, dt}      (src/point_mass.cu:46-47)
     float lambda;
     float neg_inv_lambda;  // -(1/lambda), float ops         (src/point_mass.cu:518)
+    float wf[2 * kMaxAct]; // weights of the terminal cost (Cost::final_cost); == w unless
+                           // mppi_set_terminal_weights gave the final state its own
 };
 
 // Per-step control block in device memory.

@@ -106,6 +106,7 @@ struct mppi_handle {
     unsigned long long eps_step = 0;
 
     bool problem_set = false;
+    bool terminal_set = false;   // mppi_set_terminal_weights gave the final state its own weights
     bool injected = false;
     bool profiling = false;
     bool pending = false;
@@ -836,6 +837,7 @@ int mppi_set_problem(mppi_handle *h, const float *x0, const float *u, const floa
         h->h_prob.x0[i] = x0[i];
         h->h_prob.goal[i] = goal[i];
         h->h_prob.w[i] = w[i];
+        if (!h->terminal_set) h->h_prob.wf[i] = w[i];    // one Cost object: src/point_mass_gpu.cu:116
     }
     if ((rc = upload_problem(h)) != MPPI_OK) return rc;
     CK(cudaMemcpyAsync(h->d_U, u, sizeof(float) * h->R, cudaMemcpyHostToDevice, h->stream));
@@ -843,6 +845,23 @@ int mppi_set_problem(mppi_handle *h, const float *x0, const float *u, const floa
     CK(cudaStreamSynchronize(h->stream));
     h->problem_set = true;
     return MPPI_OK;
+}
+
+int mppi_set_terminal_weights(mppi_handle *h, const float *w_final)
+{
+    if (h && !h->children.empty()) {
+        for (mppi_handle *c : h->children) {
+            int rcc = mppi_set_terminal_weights(c, w_final);
+            if (rcc) return rcc;
+        }
+        return MPPI_OK;
+    }
+    int rc = check_handle(h);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->terminal_set = w_final != nullptr;
+    for (int i = 0; i < h->S; ++i) h->h_prob.wf[i] = w_final ? w_final[i] : h->h_prob.w[i];
+    return upload_problem(h);
 }
 
 int mppi_set_u(mppi_handle *h, const float *u)

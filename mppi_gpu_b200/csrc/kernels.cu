@@ -222,11 +222,11 @@ rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
         if constexpr (PACKED) {
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
-                c2[j] = add2(c2[j], m2.state_cost(x2[j], mk2(0.0f, 0.0f)));
+                c2[j] = add2(c2[j], m2.terminal_cost(x2[j], prob));
                 un2(c2[j], c[2 * j], c[(2 * j + 1) % SPT]);
             }
         } else {
-            c[0] = __fadd_rn(c1, m1.state_cost(x1, 0.0f));
+            c[0] = __fadd_rn(c1, m1.terminal_cost(x1, prob));
         }
 #pragma unroll
         for (int j = 0; j < SPT; ++j) {
@@ -367,7 +367,7 @@ rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long
                 if (lane == 0) mbar_arrive(&empty_bar[stage]);
                 if (++stage == kRtStages) { stage = 0; phase ^= 1; }
             }
-            c = __fadd_rn(c, m.state_cost(x, 0.0f));          // src/point_mass_gpu.cu:116
+            c = __fadd_rn(c, m.terminal_cost(x, prob));        // src/point_mass_gpu.cu:116
             const long long k = (long long)slab * W + threadIdx.x;
             S[k] = c;
             if (k < k_local) {

@@ -199,6 +199,36 @@ struct QuadraticCost {
         }
         return res;
     }
+    // terminal cost, Cost::final_cost (src/cost.cu:57-64), with the weights of the Cost object the
+    // final state is charged by: wf -- the stage weights again in the reference (one object,
+    // src/point_mass_gpu.cu:116), a second object's after mppi_set_terminal_weights.  Read from
+    // memory here, once per rollout, so that they cost the T loop no registers.
+    template <bool STRICT>
+    __device__ __forceinline__ float terminal(const float (&x)[2 * A], const float *__restrict__ wf) const
+    {
+        float res = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 2 * A; ++i) {
+            const float d = __fsub_rn(x[i], goal[i]);
+            const float wi = wf[i];
+            if (STRICT) res = __fadd_rn(res, __fmul_rn(__fmul_rn(d, wi), d));
+            else        res = __fmaf_rn(__fmul_rn(d, wi), d, res);
+        }
+        return res;
+    }
+    template <bool STRICT>
+    __device__ __forceinline__ f2 terminal2(const f2 (&x)[2 * A], const float *__restrict__ wf) const
+    {
+        f2 res = mk2(0.0f, 0.0f);
+#pragma unroll
+        for (int i = 0; i < 2 * A; ++i) {
+            const f2 d = sub2(x[i], goal2[i]);
+            const f2 wi = mk2(wf[i], wf[i]);
+            if (STRICT) res = add2(res, mulp2(mul2(d, wi), d));
+            else        res = fma2(mul2(d, wi), d, res);
+        }
+        return res;
+    }
     // one term of the control cost, accumulated in action order
     template <bool STRICT>
     __device__ __forceinline__ float control(float res, float ui, float e) const
@@ -249,6 +279,11 @@ struct PointMass {
     {
         return cost.template state<STRICT>(x, res);
     }
+    __device__ __forceinline__ float terminal_cost(const float (&x)[2 * A],
+                                                   const ProblemDev *__restrict__ p) const
+    {
+        return cost.template terminal<STRICT>(x, p->wf);
+    }
     __device__ __forceinline__ void step(float (&x)[2 * A], float &c, const float (&u)[A],
                                          const float (&ui)[A], const float (&e)[A]) const
     {
@@ -278,6 +313,11 @@ struct PointMass2 {
     __device__ __forceinline__ f2 state_cost(const f2 (&x)[2 * A], f2 res) const
     {
         return cost.template state2<STRICT>(x, res);
+    }
+    __device__ __forceinline__ f2 terminal_cost(const f2 (&x)[2 * A],
+                                                const ProblemDev *__restrict__ p) const
+    {
+        return cost.template terminal2<STRICT>(x, p->wf);
     }
     __device__ __forceinline__ void step(f2 (&x)[2 * A], f2 &c, const f2 (&u)[A], const f2 (&ui)[A],
                                          const f2 (&e)[A]) const

@@ -246,7 +246,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap_eps, float *__restrict__ ep
             float c[4];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                c2[j] = add2(c2[j], m2.state_cost(x2[j], mk2(0.0f, 0.0f)));
+                c2[j] = add2(c2[j], m2.terminal_cost(x2[j], prob));
                 un2(c2[j], c[2 * j], c[2 * j + 1]);
             }
             *reinterpret_cast<float4 *>(S + 4 * g) = make_float4(c[0], c[1], c[2], c[3]);

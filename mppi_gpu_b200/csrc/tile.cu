@@ -267,7 +267,7 @@ tile_kernel(long long k_local, int T, const float *__restrict__ U,
             }
             // terminal cost on x[T], charged on top of the last stage cost
             // (src/point_mass_gpu.cu:116)
-            c2 = add2(c2, m2.state_cost(x2, mk2(0.0f, 0.0f)));
+            c2 = add2(c2, m2.terminal_cost(x2, prob));
             float s0, s1;
             un2(c2, s0, s1);
             const long long k0 = tile * kTlW + 2 * lane;

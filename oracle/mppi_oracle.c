@@ -67,21 +67,24 @@ static float step_cost_fma(const oracle_problem *p, const float *x, const float 
     return res;
 }
 
-/* Cost::final_cost, src/cost.cu:57-64 */
+/* Cost::final_cost, src/cost.cu:57-64.  The weights are those of the Cost object it is called
+ * on: w (the reference's single object) or, with use_wf, the terminal weights wf. */
 static float final_cost_strict(const oracle_problem *p, const float *x)
 {
+    const float *w = p->use_wf ? p->wf : p->w;
     float res = 0.0f;
     for (int i = 0; i < 2 * p->A; i++)
-        res += (x[i] - p->goal[i]) * p->w[i] * (x[i] - p->goal[i]);
+        res += (x[i] - p->goal[i]) * w[i] * (x[i] - p->goal[i]);
     return res;
 }
 
 static float final_cost_fma(const oracle_problem *p, const float *x)
 {
+    const float *w = p->use_wf ? p->wf : p->w;
     float res = 0.0f;
     for (int i = 0; i < 2 * p->A; i++) {
         float d = x[i] - p->goal[i];
-        res = fmaf(d * p->w[i], d, res);
+        res = fmaf(d * w[i], d, res);
     }
     return res;
 }

@@ -47,6 +47,11 @@ typedef struct oracle_problem {
                                         PointMassModelGpu::init, src/point_mass_gpu.cu:25-39) */
     float   g[4];
     float   b[2];
+    int32_t use_wf;                  /* 0: the terminal cost uses w (the reference: one Cost
+                                        object for stage and final cost, src/point_mass_gpu.cu:107,116);
+                                        1: a second Cost object with weights wf charges the final
+                                        state (Cost::final_cost, src/cost.cu:57-64, unchanged) */
+    float   wf[2 * ORACLE_MAX_ACT];
 } oracle_problem;
 
 /* gains of the double integrator: src/point_mass.cu:46-51 */

@@ -28,13 +28,22 @@ class OracleProblem(C.Structure):
         ("use_gains", C.c_int32),
         ("g", C.c_float * 4),
         ("b", C.c_float * 2),
+        ("use_wf", C.c_int32),
+        ("wf", C.c_float * (2 * MAX_ACT)),
     ]
 
 
-def make_problem(K, T, A, dt, goal, w, lam=1.0, inv_s=None, arith=ARITH_STRICT, gains=None):
+def make_problem(K, T, A, dt, goal, w, lam=1.0, inv_s=None, arith=ARITH_STRICT, gains=None,
+                 w_final=None):
     """gains = (state_gain[4], act_gain[2]) selects caller-given gains (the arguments of the
-    reference's PointMassModelGpu::init) instead of the double integrator formed from dt."""
+    reference's PointMassModelGpu::init) instead of the double integrator formed from dt.
+    w_final = weights of a second Cost object that charges the final state (Cost::final_cost);
+    None: the reference's single object, w."""
     p = OracleProblem()
+    if w_final is not None:
+        p.use_wf = 1
+        for i in range(2 * A):
+            p.wf[i] = float(w_final[i])
     if gains is not None:
         p.use_gains = 1
         for i in range(4):
@@ -113,6 +122,9 @@ def ref():
                                               _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p,
                                               C.c_int]
         L.ref_rollout_costs_gains.restype = C.c_int
+        L.ref_cost_terms.argtypes = [C.c_int, C.c_int, _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p,
+                                     _f32p, _f32p, _f32p]
+        L.ref_cost_terms.restype = C.c_int
         _ref = L
     return _ref
 
@@ -154,6 +166,17 @@ def ref_rollout_all(K, T, A, dt, lam, x0, U, goal, w, eps, want_traj=False, nthr
                                  int(nthreads))
     assert rc == 0
     return (S, xt) if want_traj else S
+
+
+def ref_cost_terms(A, w, goal, lam, inv_s, x, u, e):
+    """The reference's own Cost class (oracle/_ref): (step_cost, final_cost) of n triples
+    x [n,2A], u [n,A], e [n,A] for the weights w."""
+    x, u, e = _f32(x).reshape(-1, 2 * A), _f32(u).reshape(-1, A), _f32(e).reshape(-1, A)
+    n = x.shape[0]
+    st, fi = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    rc = ref().ref_cost_terms(n, int(A), _f32(w), _f32(goal), float(lam), _f32(inv_s), x, u, e, st, fi)
+    assert rc == 0
+    return st, fi
 
 
 def beta(S):

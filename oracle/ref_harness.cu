@@ -158,4 +158,25 @@ static int ref_rollout_costs_impl(int K, int T, int A, float *state, float *act,
 
 int ref_sizeof_model(void) { return (int)sizeof(PointMassModelGpu); }
 
+/* The reference's Cost object on its own (include/cost.hpp, src/cost.cu:42-64): step_cost and
+ * final_cost of n independent (x [2A], u [A], e [A]) triples for the weights w.  Pins the
+ * oracle's terminal-weight mode: a rollout charged with Cost(w).step_cost per step and
+ * Cost(w_final).final_cost on the last state is recomposed from these two calls. */
+int ref_cost_terms(int n, int A, const float *w_in, const float *goal_in, float lambda,
+                   const float *inv_s_in, const float *x, const float *u, const float *e,
+                   float *step_out, float *final_out)
+{
+    const int S = 2 * A;
+    std::vector<float> w(w_in, w_in + S), goal(goal_in, goal_in + S), inv_s(inv_s_in, inv_s_in + A);
+    Cost c(w.data(), S, goal.data(), S, lambda, inv_s.data(), A);
+    for (int i = 0; i < n; i++) {
+        std::vector<float> xi(x + (size_t)i * S, x + (size_t)(i + 1) * S);
+        std::vector<float> ui(u + (size_t)i * A, u + (size_t)(i + 1) * A);
+        std::vector<float> ei(e + (size_t)i * A, e + (size_t)(i + 1) * A);
+        if (step_out) step_out[i] = c.step_cost(xi.data(), ui.data(), ei.data(), 0, 0);
+        if (final_out) final_out[i] = c.final_cost(xi.data(), 0);
+    }
+    return 0;
+}
+
 }  /* extern "C" */

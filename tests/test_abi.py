@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_layout():
     lib = capi.load()
-    assert lib.mppi_abi_version() == 2
+    assert lib.mppi_abi_version() == 3
     p = capi.MppiParams()
     assert lib.mppi_params_default(C.byref(p)) == 0
     # the C side wrote sizeof(mppi_params): the ctypes mirror must agree

@@ -87,6 +87,39 @@ def test_oracle_general_gains_match_ref_bit_exact(oracle, A, K, T):
     assert np.array_equal(got[1], ref[1])
 
 
+@pytest.mark.parametrize("A,K,T", [(1, 100, 40), (2, 128, 50), (3, 64, 37)])
+def test_oracle_terminal_weights_match_the_reference_cost_class(oracle, A, K, T):
+    """Terminal weights: a second Cost object charges the final state.  The reference uses ONE
+    object for stage and final cost (src/point_mass_gpu.cu:107,116), but its Cost class takes the
+    weights as an argument (include/cost.hpp:8-14), so the class itself pins the mode: a rollout is
+    recomposed, bit for bit, from Cost(w).step_cost over the reference's own trajectory and
+    Cost(w_final).final_cost on its last state, accumulated as run() does (`_c += ...`)."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    cfg = REF_CFG[A]
+    rng = np.random.default_rng(7 * A + K)
+    wf = rng.uniform(2.0, 60.0, 2 * A).astype(np.float32)
+    lam = 0.7
+    x0, U, eps = make_inputs(K, T, A, seed=5 * K + A, sigma=0.1)
+    _, xt = oracle.ref_rollout_all(K, T, A, 0.1, lam, x0, U, cfg["goal"], cfg["w"], eps, want_traj=True)
+    p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], lam=lam, w_final=wf)
+    S = oracle.rollout_all(p, x0, U, eps)
+    inv_s = np.ones(A, np.float32)
+    want = np.zeros(K, np.float32)
+    for k in range(K):
+        st, _ = oracle.ref_cost_terms(A, cfg["w"], cfg["goal"], lam, inv_s, xt[k, 1:], U, eps[k])
+        _, fi = oracle.ref_cost_terms(A, wf, cfg["goal"], lam, inv_s, xt[k, T:], U[:1], eps[k, :1])
+        c = np.float32(0)
+        for t in range(T):
+            c = np.float32(c + st[t])
+        want[k] = np.float32(c + fi[0])
+    assert np.array_equal(bits(S), bits(want))
+    # and with w_final == w the mode is the reference's run()
+    p2 = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], lam=lam, w_final=cfg["w"])
+    p1 = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], lam=lam)
+    assert np.array_equal(bits(oracle.rollout_all(p2, x0, U, eps)), bits(oracle.rollout_all(p1, x0, U, eps)))
+
+
 def test_fma_and_strict_agree_to_rounding(oracle):
     g = load_golden("pm3d")
     rel = np.abs(g["S_fma"] - g["S_ref"]) / np.abs(g["S_ref"])
