@@ -245,8 +245,12 @@ int enqueue_chain(mppi_handle *h, bool sample, cudaEvent_t *evs)
     // single shard, or peer-mailbox shards merging with one exchange: the last CTA of the
     // averaging kernel finishes the step (exchange included) -- no kernel behind it
     const bool merge_fin = !split && (!multi(h) || one_xchg);
+    // the rollout kernel is directly in front of the average unless a collective or the weights
+    // kernel sits between them: programmatic dependent launch of the average
+    bool pdl = !split && !(multi(h) && !one_xchg);
+    if (const char *env = getenv("MPPI_PDL")) pdl = pdl && atoi(env) != 0;
     CK(launch_average(c, h->tmap, split ? h->d_wt : h->d_S, h->d_acc, !split, merge_fin, h->d_prob,
-                      h->d_ctl, h->d_U, h->d_Uprev, h->d_next, h->p.flags, xa));
+                      h->d_ctl, h->d_U, h->d_Uprev, h->d_next, h->p.flags, xa, pdl));
     CK(mark());
     if (one_xchg) {
         // nothing: exchanged and finalized inside the averaging kernel

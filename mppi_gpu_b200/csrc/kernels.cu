@@ -83,6 +83,9 @@ rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
     constexpr int UST = PACKED ? UStage2<A>::kStride : UStage<A>::kStride;
     extern __shared__ __align__(16) float smem_f[];          // [T][UST]
     __shared__ unsigned long long s_key[8];
+    // the averaging kernel behind this one may be scheduled as soon as SMs have room for it; it
+    // waits (griddepcontrol.wait) for this grid to finish before it reads anything
+    asm volatile("griddepcontrol.launch_dependents;");
 
     for (int i = threadIdx.x; i < T * A; i += blockDim.x) {
         const float u = U[i];
@@ -293,6 +296,7 @@ rollout_tma_kernel(const __grid_constant__ CUtensorMap tmap_eps, int nslab, long
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_u + (size_t)T * UST);
     uint64_t *empty_bar = full_bar + kRtStages;
     __shared__ unsigned long long s_key[kRtConsumerWarps];
+    asm volatile("griddepcontrol.launch_dependents;");        // see rollout_kernel
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < T * A; i += blockDim.x) {
@@ -489,6 +493,11 @@ average_kernel(const __grid_constant__ CUtensorMap tmap_eps, const float *__rest
         fence_proxy_async();
     }
     __syncthreads();
+    // Programmatic dependent launch: when launched with the attribute (launch_average, pdl), this
+    // grid may start while the rollout kernel in front of it is still running -- barrier
+    // initialisation and the zeroing above overlap its tail -- and everything the rollout wrote
+    // (eps, S, the min key) is only touched behind this point.  Without the attribute: a no-op.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // static, balanced partition of the slab-major tile list
     const long long ntiles = (long long)nslab * nchunk;
@@ -1018,15 +1027,27 @@ cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev 
 cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *src,
                            long long *acc, bool merge_weights, bool merge_finalize,
                            const ProblemDev *prob, CtlDev *ctl, float *U, float *U_prev,
-                           float *next_act, unsigned flags, const XchgArgs &xa)
+                           float *next_act, unsigned flags, const XchgArgs &xa, bool pdl)
 {
     const size_t smem = average_smem_bytes(c.rows);
     const int nslab = (int)(c.k_pad / kAvgTileK);
     const int nchunk = (c.rows + kAvgTileR - 1) / kAvgTileR;
     FinalizeArgs fin{U, U_prev, next_act, c.horizon, c.act_dim, flags};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)c.avg_grid);
+    cfg.blockDim = dim3(kAvgThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const long long k_local = (long long)c.k_local;
+    const int rows = c.rows;
 #define MPPI_AVG_LAUNCH(MW, MF)                                                                  \
-    average_kernel<MW, MF><<<c.avg_grid, kAvgThreads, smem, c.stream>>>(                         \
-        tmap_eps, src, acc, c.rows, nslab, nchunk, (long long)c.k_local, prob, ctl, fin, xa)
+    return cudaLaunchKernelEx(&cfg, average_kernel<MW, MF>, tmap_eps, src, acc, rows, nslab, nchunk, \
+                              k_local, prob, ctl, fin, xa)
     if (merge_weights && merge_finalize) MPPI_AVG_LAUNCH(true, true);
     else if (merge_weights)              MPPI_AVG_LAUNCH(true, false);
     else if (merge_finalize)             MPPI_AVG_LAUNCH(false, true);

@@ -70,7 +70,9 @@ cudaError_t launch_weights(const LaunchCtx &c, const float *S, const ProblemDev 
 cudaError_t launch_average(const LaunchCtx &c, const CUtensorMap &tmap_eps, const float *src,
                            long long *acc, bool merge_weights, bool merge_finalize,
                            const ProblemDev *prob, CtlDev *ctl, float *U, float *U_prev,
-                           float *next_act, unsigned flags, const XchgArgs &xa);
+                           float *next_act, unsigned flags, const XchgArgs &xa, bool pdl = false);
+//     pdl: the kernel launched in front of it on the same stream is one of the rollout kernels
+//          (no collective, no weights kernel in between): programmatic dependent launch
 
 // (5) U += acc[0..R-1]/acc[R]; shift, next_act, advance step, re-arm acc and min key
 cudaError_t launch_finalize(const LaunchCtx &c, long long *acc, float *U, float *U_prev,
