@@ -20,10 +20,11 @@ for A in (1, 2, 3):
     for K in (1000, 10000, 100000, 1000000, 10000000):
         steps = 200 if K <= 100000 else (30 if K <= 1000000 else 8)
         best = None
-        for flags in (0, capi.FLAG_FUSED_SAMPLING, capi.FLAG_STEP_KERNEL):
+        for flags in (0, capi.FLAG_FUSED_SAMPLING, capi.FLAG_STEP_KERNEL, capi.FLAG_AUTO_CHAIN):
             if flags == capi.FLAG_STEP_KERNEL and K < 100000:
                 continue
             ctl = m.PointMassModel(K, T, 0.1, 2 * A, A, flags=flags)
+            resolved = ctl.flags()
             ctl.memcpy_set_data(np.zeros(2 * A), np.zeros(T * A), *CFG[A])
             for _ in range(5):
                 ctl.get_act()
@@ -38,7 +39,7 @@ for A in (1, 2, 3):
             kt = {k: t / n for k, (t, n) in ctl.kernel_times().items() if n}
             ctl.close()
             eps_bytes = 4.0 * K * T * A
-            row = {"A": A, "K": K, "T": T, "flags": flags, "ms_per_step": ms,
+            row = {"A": A, "K": K, "T": T, "flags": flags, "resolved_flags": resolved, "ms_per_step": ms,
                    "rollout_steps_per_s": K * T / (ms * 1e-3),
                    "step_hbm_frac_of_3_pass_roofline": (3 * eps_bytes + 16.0 * K) / (ms * 1e-3) / 1e9 / PEAK,
                    "step_hbm_frac_of_2_pass_roofline": (2 * eps_bytes + 8.0 * K) / (ms * 1e-3) / 1e9 / PEAK,
