@@ -636,10 +636,13 @@ def run_ours(args, name, K, T, A, dt, goal, w):
         for cname, cflags in (("tile_kernel_eps_on_chip", base | capi.FLAG_TILE_KERNEL),
                               ("step_kernel_eps_via_hbm", base | capi.FLAG_STEP_KERNEL),
                               ("fused_2_kernels", base | capi.FLAG_FUSED_SAMPLING),
-                              ("unfused_3_kernels", base)):
-            if cflags == flags:
+                              ("unfused_3_kernels", base),
+                              # an OPTION, not the headline: Philox-4x32-7 (mppi_params.philox_rounds)
+                              ("fused_2_kernels_philox7", base | capi.FLAG_FUSED_SAMPLING)):
+            if cflags == flags and not cname.endswith("philox7"):
                 continue
-            c2 = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=cflags, device=local_rank)
+            c2 = m.PointMassModel(K, T, dt, 2 * A, A, seed=0, flags=cflags, device=local_rank,
+                                  philox_rounds=7 if cname.endswith("philox7") else 10)
             c2.memcpy_set_data(x0, np.zeros((T, A), np.float32), goal, w)
             for _ in range(3):
                 c2.get_act()
@@ -665,7 +668,7 @@ def run_ours(args, name, K, T, A, dt, goal, w):
             if not one:
                 if "sample" in kt4:
                     others[cname]["kernels"]["sample"]["fma_pipe"] = fma_pipe(kt4["sample"], False, True)
-                if "rollout" in kt4 and (cflags & capi.FLAG_FUSED_SAMPLING):
+                if "rollout" in kt4 and (cflags & capi.FLAG_FUSED_SAMPLING) and not cname.endswith("philox7"):
                     others[cname]["kernels"]["rollout"]["fma_pipe"] = fma_pipe(kt4["rollout"], True, True)
         out["other_chains"] = others
     if world > 1:

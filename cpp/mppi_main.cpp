@@ -3,6 +3,7 @@
 //   mppi_main -c <config.yaml> [-t traj.csv] [-s step_prefix] [--plant ideal|mjcf] [--steps N] [--samples K]
 //             [--horizon T] [--honour-config] [--seed S] [--devices 0,1,..] [--verify-config] [--quiet]
 //             [--model ideal|mjcf] [--plant-us N] [--flags BITS [--exact-flags]] [--terminal-w w0,w1,..]
+//             [--philox-rounds 7|10]
 //
 // --plant-us N makes the plant's turn take N microseconds of host time (the reference steps
 // MuJoCo there); --flags adds MPPI_FLAG_* bits to the default MPPI_FLAG_AUTO_CHAIN;
@@ -114,6 +115,7 @@ int main(int argc, char **argv)
     unsigned extra_flags = 0;      // MPPI_FLAG_* bits on top of the default (auto chain)
     bool exact_flags = false;
     std::vector<float> terminal_w;
+    int philox_rounds = 10;
     std::vector<int> devices;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -133,6 +135,7 @@ int main(int argc, char **argv)
         else if (a == "--plant-us") plant_us = std::stol(next());
         else if (a == "--flags") extra_flags = (unsigned)std::stoul(next(), nullptr, 0);
         else if (a == "--exact-flags") exact_flags = true;   // --flags replaces the default
+        else if (a == "--philox-rounds") philox_rounds = std::stoi(next());
         else if (a == "--terminal-w") {
             std::string list = next();
             size_t pos = 0;
@@ -180,6 +183,7 @@ int main(int argc, char **argv)
 
     PointMassModel::Options opt;
     opt.seed = seed;
+    opt.philox_rounds = philox_rounds;
     opt.flags = exact_flags ? extra_flags : (opt.flags | extra_flags);
     if (!devices.empty()) { opt.devices = devices.data(); opt.num_devices = (int)devices.size(); }
     float state_gain[4], act_gain[2];

@@ -154,7 +154,12 @@ typedef struct mppi_params {
     int32_t  model;                     /* MPPI_MODEL_*                               */
     float    state_gain[4];             /* {g0,g1,g2,g3}, MPPI_MODEL_LINEAR_AXIS only */
     float    act_gain[2];               /* {b0,b1},       MPPI_MODEL_LINEAR_AXIS only */
-    int32_t  reserved_;
+    int32_t  philox_rounds;             /* 0 or 10: Philox-4x32-10 (default); 7: Philox-4x32-7,
+                                           Random123's crush-resistant minimum -- 30 % fewer of
+                                           the multiplies that bound the sampling kernels (-13 % on
+                                           the fused rollout).  The kernel chains only: with 7 the
+                                           one-kernel steps are not used (MPPI_FLAG_STEP_KERNEL /
+                                           MPPI_FLAG_TILE_KERNEL fall back to the fused chain)    */
 } mppi_params;
 
 /* per-step scalars, the reference's _beta / _nabla (src/point_mass.cu:250-257) */

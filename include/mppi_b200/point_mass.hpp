@@ -47,6 +47,7 @@ public:
                                            // double integrator formed from dt
         const int *devices = nullptr;      // non-null: shard K over these GPUs (one process)
         int num_devices = 0;
+        int philox_rounds = 10;            // 7: Philox-4x32-7 (kernel chains only, see mppi_params)
     };
 
     PointMassModel(int nb_sim, int steps, float dt, int state_dim, int act_dim,
@@ -68,6 +69,7 @@ public:
         p.seed = o.seed;
         p.flags = o.flags;
         p.device = o.device;
+        p.philox_rounds = o.philox_rounds;
         for (int a = 0; a < act_dim && a < MPPI_MAX_ACT; ++a) {
             if (o.sigma) p.sigma[a] = o.sigma[a];
             if (o.inv_sigma) p.inv_sigma[a] = o.inv_sigma[a];

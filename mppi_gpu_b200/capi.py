@@ -76,7 +76,7 @@ class MppiParams(C.Structure):
         ("model", C.c_int32),
         ("state_gain", C.c_float * 4),
         ("act_gain", C.c_float * 2),
-        ("reserved_", C.c_int32),
+        ("philox_rounds", C.c_int32),
     ]
 
 

@@ -21,7 +21,7 @@ class PointMassModel:
     def __init__(self, nb_sim, steps, dt, state_dim, act_dim, verbose=False, *, lam=1.0,
                  sigma=0.025, inv_sigma=1.0, init_act=0.0, max_act=1.0, seed=0, flags=0,
                  device=0, rank=0, world_size=1, comm_id=None, comm=None, devices=None,
-                 state_gain=None, act_gain=None):
+                 state_gain=None, act_gain=None, philox_rounds=10):
         self._lib = capi.load()
         p = capi.MppiParams()
         capi.check(self._lib.mppi_params_default(C.byref(p)))
@@ -35,6 +35,7 @@ class PointMassModel:
             for i, v in enumerate(arr):
                 getattr(p, name)[i] = float(v)
         p.seed, p.flags, p.device = int(seed), int(flags), int(device)
+        p.philox_rounds = int(philox_rounds)
         if state_gain is not None or act_gain is not None:
             # MPPI_MODEL_LINEAR_AXIS: caller-given gains {g0,g1,g2,g3}, {b0,b1}
             assert len(state_gain) == 4 and len(act_gain) == 2

@@ -526,6 +526,8 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     if (p.horizon < 1 || (long long)p.horizon * p.act_dim > 32768)
         return fail(MPPI_ERR_INVALID, "horizon %d out of range", p.horizon);
     if (!(p.lambda > 0.0f)) return fail(MPPI_ERR_INVALID, "lambda must be > 0");
+    if (p.philox_rounds != 0 && p.philox_rounds != 7 && p.philox_rounds != 10)
+        return fail(MPPI_ERR_INVALID, "philox_rounds %d: 10 (or 0) and 7 exist", p.philox_rounds);
     if (p.model != MPPI_MODEL_POINT_MASS && p.model != MPPI_MODEL_LINEAR_AXIS)
         return fail(MPPI_ERR_INVALID, "model %d unknown", p.model);
     if (p.world_size < 1 || p.rank < 0 || p.rank >= p.world_size)
@@ -551,6 +553,9 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
 
     mppi_handle *h = new mppi_handle();
     h->p = p;
+    // seven Philox rounds exist in the kernel chains only: a one-kernel request becomes the fused chain
+    if (p.philox_rounds == 7 && (p.flags & (MPPI_FLAG_STEP_KERNEL | MPPI_FLAG_TILE_KERNEL)))
+        h->p.flags = (p.flags & ~(uint32_t)(MPPI_FLAG_STEP_KERNEL | MPPI_FLAG_TILE_KERNEL)) | MPPI_FLAG_FUSED_SAMPLING;
     h->R = p.horizon * p.act_dim;
     h->S = p.state_dim;
     h->injected = (p.flags & MPPI_FLAG_INJECTED_NOISE) != 0;
@@ -576,6 +581,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     c.avg_grid = (int)(ntiles < c.num_sms ? ntiles : c.num_sms);
     c.weights_blocks = (int)((c.k_pad + kWeightsBlockSamples - 1) / kWeightsBlockSamples);
     c.sampler = make_sampler_params(p.seed, p.sigma, p.act_dim);
+    c.philox_rounds = p.philox_rounds == 7 ? 7 : 10;
     // samples per rollout thread: wide vectors once there are enough samples for many waves
     {
         const double waves4 = (double)c.k_pad / 4.0 / (512.0 * c.num_sms);
@@ -623,7 +629,9 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     // 240 GB at K=1e8, T=200, A=3, more than the GPU has) is only allocated if something asks
     // for the noise in memory (injected noise, the eps / trajectory taps, mppi_sample_only):
     // ensure_eps().  Every other chain needs it from the first step.
-    h->tile_ok = (p.flags & MPPI_FLAG_TILE_KERNEL) && !(p.flags & MPPI_FLAG_SPLIT_KERNELS) &&
+    // the one-kernel steps exist with ten Philox rounds only (philox_rounds = 7: kernel chains)
+    const bool ten_rounds = p.philox_rounds != 7;
+    h->tile_ok = ten_rounds && (p.flags & MPPI_FLAG_TILE_KERNEL) && !(p.flags & MPPI_FLAG_SPLIT_KERNELS) &&
                  !(p.flags & MPPI_FLAG_INJECTED_NOISE) && (p.world_size == 1 || p.comm == MPPI_COMM_P2P) &&
                  tile_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms);
     if (!h->tile_ok) CKH(cudaMalloc(&h->d_eps, eps_bytes));
@@ -669,7 +677,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
     }
     CKH(configure_kernels(c));
     if (p.flags & MPPI_FLAG_AUTO_CHAIN) {
-        const bool can_step = (p.world_size == 1 || p.comm == MPPI_COMM_P2P) &&
+        const bool can_step = ten_rounds && (p.world_size == 1 || p.comm == MPPI_COMM_P2P) &&
                               step_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms);
         if (!(p.flags & MPPI_FLAG_SPLIT_KERNELS)) h->p.flags |= auto_chain(c, can_step);
         h->p.flags &= ~MPPI_FLAG_AUTO_CHAIN;
@@ -686,7 +694,7 @@ int mppi_create(const mppi_params *params, mppi_handle **out)
         h->eps_base[1] = h->d_eps_alt;
         CKH(cudaMemsetAsync(h->d_eps_alt, 0, eps_bytes, h->stream));
     }
-    h->step_ok = (h->p.flags & MPPI_FLAG_STEP_KERNEL) &&
+    h->step_ok = ten_rounds && (h->p.flags & MPPI_FLAG_STEP_KERNEL) &&
                  step_kernel_supported(p.horizon, p.act_dim, c.k_pad, c.num_sms);
     if (h->step_ok) CKH(configure_step(c));
     if (h->tile_ok) CKH(configure_tile(c));

@@ -25,7 +25,7 @@ namespace mppi {
 //     consecutive time steps; per (t,a) one Philox call -> one 16-byte store, 512 B per
 //     warp and row.  No per-row branches: the action index is the unrolled inner loop.
 // =================================================================================
-template <int A>
+template <int A, int ROUNDS>
 __global__ void __launch_bounds__(256)
 sample_kernel(float *__restrict__ eps, size_t ld, int T, int t_per_cta,
               const CtlDev *__restrict__ ctl, unsigned long long k_offset,
@@ -44,7 +44,7 @@ sample_kernel(float *__restrict__ eps, size_t ld, int T, int t_per_cta,
     for (int t = t0; t < t1; ++t) {
 #pragma unroll
         for (int a = 0; a < A; ++a) {
-            stg_f4(p, sample4(qg, r, step, sp, sp.c[a]));
+            stg_f4(p, sample4<ROUNDS>(qg, r, step, sp, sp.c[a]));
             p += ld;
             ++r;
         }
@@ -69,7 +69,7 @@ sample_kernel(float *__restrict__ eps, size_t ld, int T, int t_per_cta,
 // steps through a register double buffer: the loads of chunk c+1 are issued before the
 // arithmetic of chunk c, so every thread keeps CH*A vector loads (96 B for A=3) in flight.
 // SPT >= 2: the samples advance in pairs on the packed FP32x2 path (PointMass2).
-template <int A, class MODEL, bool FUSED, int SPT>
+template <int A, class MODEL, bool FUSED, int SPT, int ROUNDS = 10>
 __global__ void __launch_bounds__(256, (SPT == 1 ? 3 : 2))
 rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
                const float *__restrict__ U, const ProblemDev *__restrict__ prob,
@@ -156,7 +156,7 @@ rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
             // the two dependent chains interleave inside one loop body.  -3 % on this kernel.
             float4 nn[A];
 #pragma unroll
-            for (int a = 0; a < A; ++a) nn[a] = sample4(qg, r++, step, sp, sp.c[a]);
+            for (int a = 0; a < A; ++a) nn[a] = sample4<ROUNDS>(qg, r++, step, sp, sp.c[a]);
 #pragma unroll 2
             for (int t = 0; t < T; ++t) {
                 float e[A][SPT];
@@ -168,7 +168,7 @@ rollout_kernel(float *__restrict__ eps, size_t ld, long long k_local, int T,
                     e[a][0] = n.x; e[a][1 % SPT] = n.y; e[a][2 % SPT] = n.z; e[a][3 % SPT] = n.w;
                 }
 #pragma unroll
-                for (int a = 0; a < A; ++a) nn[a] = sample4(qg, r++, step, sp, sp.c[a]);   // one past T: unused
+                for (int a = 0; a < A; ++a) nn[a] = sample4<ROUNDS>(qg, r++, step, sp, sp.c[a]);   // one past T: unused
                 advance(t, e);
             }
         } else {
@@ -930,14 +930,21 @@ cudaError_t launch_sample(const LaunchCtx &c, float *eps, const CtlDev *ctl,
     int tpc = (int)(((long long)c.horizon * gx) / (8ll * c.num_sms));
     tpc = tpc < 1 ? 1 : (tpc > 16 ? 16 : tpc);
     dim3 grid(gx, (unsigned)((c.horizon + tpc - 1) / tpc));
-    MPPI_DISPATCH_A(c.act_dim,
-        sample_kernel<kA><<<grid, 256, 0, c.stream>>>(eps, (size_t)c.k_pad, c.horizon, tpc, ctl,
-                                                      (unsigned long long)c.k_offset, c.sampler,
-                                                      use_step_override ? 1 : 0, step_override));
+    if (c.philox_rounds == 7) {
+        MPPI_DISPATCH_A(c.act_dim,
+            (sample_kernel<kA, 7><<<grid, 256, 0, c.stream>>>(eps, (size_t)c.k_pad, c.horizon, tpc, ctl,
+                                                             (unsigned long long)c.k_offset, c.sampler,
+                                                             use_step_override ? 1 : 0, step_override)));
+    } else {
+        MPPI_DISPATCH_A(c.act_dim,
+            (sample_kernel<kA, 10><<<grid, 256, 0, c.stream>>>(eps, (size_t)c.k_pad, c.horizon, tpc, ctl,
+                                                              (unsigned long long)c.k_offset, c.sampler,
+                                                              use_step_override ? 1 : 0, step_override)));
+    }
     return cudaGetLastError();
 }
 
-template <int A, class MODEL, bool FUSED, int SPT>
+template <int A, class MODEL, bool FUSED, int SPT, int ROUNDS = 10>
 static cudaError_t launch_rollout_t(const LaunchCtx &c, float *eps, const float *U,
                                     const ProblemDev *prob, float *S, CtlDev *ctl)
 {
@@ -947,7 +954,7 @@ static cudaError_t launch_rollout_t(const LaunchCtx &c, float *eps, const float 
     const unsigned grid = (unsigned)((groups + threads - 1) / threads);
     const size_t smem = sizeof(float) * (size_t)c.horizon *
                         (SPT >= 2 ? UStage2<A>::kStride : UStage<A>::kStride);
-    rollout_kernel<A, MODEL, FUSED, SPT><<<grid, threads, smem, c.stream>>>(
+    rollout_kernel<A, MODEL, FUSED, SPT, ROUNDS><<<grid, threads, smem, c.stream>>>(
         eps, (size_t)c.k_pad, (long long)c.k_local, c.horizon, U, prob, S, ctl,
         (unsigned long long)c.k_offset, c.sampler);
     return cudaGetLastError();
@@ -957,7 +964,9 @@ template <int A, class MODEL>
 static cudaError_t launch_rollout_a(const LaunchCtx &c, float *eps, const float *U,
                                     const ProblemDev *prob, float *S, CtlDev *ctl, bool fused)
 {
-    if (fused) return launch_rollout_t<A, MODEL, true, 4>(c, eps, U, prob, S, ctl);
+    if (fused)
+        return c.philox_rounds == 7 ? launch_rollout_t<A, MODEL, true, 4, 7>(c, eps, U, prob, S, ctl)
+                                    : launch_rollout_t<A, MODEL, true, 4>(c, eps, U, prob, S, ctl);
     switch (c.rollout_spt) {
         case 1: return launch_rollout_t<A, MODEL, false, 1>(c, eps, U, prob, S, ctl);
         case 2: return launch_rollout_t<A, MODEL, false, 2>(c, eps, U, prob, S, ctl);
@@ -1150,6 +1159,7 @@ static cudaError_t configure_rollout_s()
 {
     cudaError_t e;
     if ((e = opt_in(rollout_kernel<A, MODEL, true, 4>)) != cudaSuccess) return e;
+    if ((e = opt_in(rollout_kernel<A, MODEL, true, 4, 7>)) != cudaSuccess) return e;
     if ((e = opt_in(rollout_kernel<A, MODEL, false, 4>)) != cudaSuccess) return e;
     if ((e = opt_in(rollout_kernel<A, MODEL, false, 2>)) != cudaSuccess) return e;
     if ((e = opt_in(rollout_kernel<A, MODEL, false, 1>)) != cudaSuccess) return e;

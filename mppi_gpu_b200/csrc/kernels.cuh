@@ -36,6 +36,7 @@ struct LaunchCtx {
     bool rollout_tma;      // use the TMA-staged rollout kernel (injected / unfused sampling)
     int  rollout_tma_width; // its slab width (TMA box inner dim): 64, 128 or 256 samples
     SamplerParams sampler; // Philox round keys of the seed, sigma-derived constants
+    int  philox_rounds;    // 10 (default) or 7: sample_kernel and the fused rollout only
 };
 
 // (1) eps[r][k] = sigma[a] * N(0,1), Philox counter (k/4, r, step)

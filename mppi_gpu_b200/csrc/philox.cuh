@@ -43,13 +43,16 @@ inline SamplerParams make_sampler_params(unsigned long long seed, const float *s
 }
 
 #ifdef __CUDACC__
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const SamplerParams &sp)
+// ROUNDS = 10 is the generator of Random123 / cuRAND (the default); 7 is Random123's
+// philox4x32_R<7>, the fewest rounds that pass BigCrush (Salmon et al., SC'11, table 2) -- 30 %
+// fewer of the 32x32->64 multiplies that bound the sampling kernels.  Same key
+// schedule, so sp.k0/k1 serve both.
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, const SamplerParams &sp)
 {
-#ifndef MPPI_PHILOX_ROUNDS
-#define MPPI_PHILOX_ROUNDS 10
-#endif
+    static_assert(ROUNDS == 7 || ROUNDS == 10, "Philox-4x32 with 7 or 10 rounds");
 #pragma unroll
-    for (int i = 0; i < MPPI_PHILOX_ROUNDS; ++i) {
+    for (int i = 0; i < ROUNDS; ++i) {
         const uint32_t hi0 = __umulhi(kPhiloxM0, c.x), lo0 = kPhiloxM0 * c.x;
         const uint32_t hi1 = __umulhi(kPhiloxM1, c.z), lo1 = kPhiloxM1 * c.z;
         c = make_uint4(hi1 ^ c.y ^ sp.k0[i], lo1, hi0 ^ c.w ^ sp.k1[i], lo0);
@@ -96,10 +99,11 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float c, fl
 }
 
 // eps of (quad q, row r, step) for the four samples 4q..4q+3, c = sp.c[a] of that row
+template <int ROUNDS = 10>
 __device__ __forceinline__ float4 sample4(uint32_t q, uint32_t r, unsigned long long step,
                                           const SamplerParams &sp, float c)
 {
-    const uint4 x = philox4x32_10(make_uint4(q, r, (uint32_t)step, (uint32_t)(step >> 32)), sp);
+    const uint4 x = philox4x32<ROUNDS>(make_uint4(q, r, (uint32_t)step, (uint32_t)(step >> 32)), sp);
     float4 n;
     box_muller(x.x, x.y, c, n.x, n.y);
     box_muller(x.z, x.w, c, n.z, n.w);

@@ -293,9 +293,16 @@ void oracle_step(const oracle_problem *p, const float *x0, float *U, const float
 
 void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {
+    oracle_philox4x32(ctr, key, 10, out);
+}
+
+/* Philox-4x32 with `rounds` rounds (Random123's philox4x32_R<rounds>; 7 and 10 have known
+ * answers in its kat_vectors) */
+void oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4])
+{
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
     uint32_t k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < rounds; r++) {
         uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
         uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -326,6 +333,12 @@ static inline void box_muller(uint32_t xa, uint32_t xb, float c, float *n0, floa
 void oracle_sample_eps(uint64_t seed, uint64_t step, int64_t k0, int64_t K, int T, int A,
                        const float *sigma, float *eps)
 {
+    oracle_sample_eps_rounds(seed, step, k0, K, T, A, sigma, 10, eps);
+}
+
+void oracle_sample_eps_rounds(uint64_t seed, uint64_t step, int64_t k0, int64_t K, int T, int A,
+                              const float *sigma, int rounds, float *eps)
+{
     const int R = T * A;
     const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
     float c[ORACLE_MAX_ACT];
@@ -338,7 +351,7 @@ void oracle_sample_eps(uint64_t seed, uint64_t step, int64_t k0, int64_t K, int 
             uint32_t ctr[4] = { q, (uint32_t)r, (uint32_t)step, (uint32_t)(step >> 32) };
             uint32_t x[4];
             float n[4];
-            oracle_philox4x32_10(ctr, key, x);
+            oracle_philox4x32(ctr, key, rounds, x);
             box_muller(x[0], x[1], c[r % A], &n[0], &n[1]);
             box_muller(x[2], x[3], c[r % A], &n[2], &n[3]);
             eps[(size_t)k * R + r] = n[lane];

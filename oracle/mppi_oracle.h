@@ -105,6 +105,8 @@ void  oracle_step(const oracle_problem *p, const float *x0, float *U,
  * Philox-4x32-10 (Salmon et al., SC'11; Random123 v1.14 known-answer vectors;
  * same round/key constants as cuRAND's curand_philox4x32_x.h, CUDA 12.9). */
 void  oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* the same with 7 or 10 rounds (mppi_params.philox_rounds) */
+void  oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]);
 
 /* The controller's noise stream: for quad q = k/4 and row r = t*A+a,
  *   (e0..e3) = BoxMuller(Philox(ctr = {q, r, step_lo, step_hi}, key = seed); sigma[a])
@@ -112,6 +114,8 @@ void  oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_
  * Writes the reference layout [K,T,A] for global samples k0 .. k0+K-1. */
 void  oracle_sample_eps(uint64_t seed, uint64_t step, int64_t k0, int64_t K, int T, int A,
                         const float *sigma, float *eps);
+void  oracle_sample_eps_rounds(uint64_t seed, uint64_t step, int64_t k0, int64_t K, int T, int A,
+                               const float *sigma, int rounds, float *eps);
 
 #ifdef __cplusplus
 }

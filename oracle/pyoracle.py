@@ -99,6 +99,10 @@ def lib():
                                            C.POINTER(C.c_uint32)]
         L.oracle_sample_eps.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int,
                                         C.c_int, _f32p, _f32p]
+        L.oracle_philox4x32.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int,
+                                        C.POINTER(C.c_uint32)]
+        L.oracle_sample_eps_rounds.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int,
+                                               C.c_int, _f32p, C.c_int, _f32p]
         _lib = L
     return _lib
 
@@ -235,16 +239,16 @@ def step(p, x0, U, eps, nthreads=1):
                 weights=w, argmin=int(am.value))
 
 
-def philox(ctr, key):
+def philox(ctr, key, rounds=10):
     c = (C.c_uint32 * 4)(*[int(x) & 0xFFFFFFFF for x in ctr])
     k = (C.c_uint32 * 2)(*[int(x) & 0xFFFFFFFF for x in key])
     o = (C.c_uint32 * 4)()
-    lib().oracle_philox4x32_10(c, k, o)
+    lib().oracle_philox4x32(c, k, int(rounds), o)
     return [int(x) for x in o]
 
 
-def sample_eps(seed, step_idx, k0, K, T, A, sigma):
+def sample_eps(seed, step_idx, k0, K, T, A, sigma, rounds=10):
     eps = np.zeros((K, T, A), np.float32)
-    lib().oracle_sample_eps(int(seed), int(step_idx), int(k0), int(K), int(T), int(A),
-                            _f32(sigma), eps)
+    lib().oracle_sample_eps_rounds(int(seed), int(step_idx), int(k0), int(K), int(T), int(A),
+                                   _f32(sigma), int(rounds), eps)
     return eps

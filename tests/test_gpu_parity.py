@@ -237,17 +237,18 @@ def test_reinit_and_clamp_flags(M, oracle):
 
 
 # ------------------------------------------------------------------ (1) sampling
+@pytest.mark.parametrize("rounds", [10, 7])
 @pytest.mark.parametrize("A", [1, 2, 3])
-def test_sampler_matches_oracle_stream(M, oracle, A):
+def test_sampler_matches_oracle_stream(M, oracle, A, rounds):
     K, T = 1027, 33
     sig = [0.025, 0.1, 0.3][:A]
-    ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, sigma=sig, seed=0x1234567890ABCDEF)
+    ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, sigma=sig, seed=0x1234567890ABCDEF, philox_rounds=rounds)
     cfg = REF_CFG[A]
     ctl.memcpy_set_data(np.zeros(2 * A), np.zeros(T * A), cfg["goal"], cfg["w"])
     for step in (0, 5, 2 ** 33 + 1):
         ctl.sample_only(step)
         e = ctl.get_inf()["e"]
-        want = oracle.sample_eps(0x1234567890ABCDEF, step, 0, K, T, A, sig)
+        want = oracle.sample_eps(0x1234567890ABCDEF, step, 0, K, T, A, sig, rounds=rounds)
         s = np.asarray(sig, np.float32)[None, None, :]
         _assert_noise_close(e, want, s)
     ctl.close()
@@ -385,3 +386,41 @@ def test_full_size_point_mass3d_properties(M, oracle):
     z = e[:: 50].astype(np.float64).ravel() / 0.025
     assert abs(z.mean()) < 5 / np.sqrt(z.size) and abs(z.std() - 1) < 2e-3
     ctl.close()
+
+
+def test_seven_round_philox_chains(M, oracle):
+    """mppi_params.philox_rounds = 7 (Random123's philox4x32_R<7>): the fused and the unfused chain
+    draw the same noise, bit for bit, and it is the oracle's 7-round stream; costs / argmin / U as
+    always; a one-kernel request (the one-kernel steps exist with ten rounds only) runs the fused chain;
+    ten rounds give a different stream."""
+    from mppi_gpu_b200 import capi
+    K, T, A = 5000, 60, 3
+    cfg = REF_CFG[A]
+    x0, U, _ = make_inputs(K, T, A, seed=29)
+    p = oracle.make_problem(K, T, A, 0.1, cfg["goal"], cfg["w"], arith=oracle.ARITH_FMA)
+    noise = {}
+    for name, flags in (("unfused", 0), ("fused", capi.FLAG_FUSED_SAMPLING), ("step", capi.FLAG_STEP_KERNEL)):
+        ctl = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=42, flags=flags, philox_rounds=7)
+        if name == "step":
+            assert ctl.flags() & capi.FLAG_FUSED_SAMPLING and not ctl.flags() & capi.FLAG_STEP_KERNEL
+        ctl.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+        for step in range(2):
+            pre = ctl.get_u()
+            na = ctl.get_act()
+            inf = ctl.get_inf()
+            info = ctl.step_info()
+            ref = oracle.step(p, x0, pre, inf["e"])
+            _assert_parity(na, inf, info, ref, K, T, A)
+            want = oracle.sample_eps(42, step, 0, K, T, A, [0.025] * A, rounds=7)
+            _assert_noise_close(inf["e"], want, 0.025)
+        noise[name] = inf["e"].copy()
+        ctl.close()
+    assert np.array_equal(bits(noise["unfused"]), bits(noise["fused"]))
+    assert np.array_equal(bits(noise["step"]), bits(noise["fused"]))
+    ten = M.PointMassModel(K, T, 0.1, 2 * A, A, seed=42, flags=capi.FLAG_FUSED_SAMPLING)
+    ten.memcpy_set_data(x0, U, cfg["goal"], cfg["w"])
+    ten.get_act(); ten.get_act()
+    assert not np.array_equal(bits(ten.get_inf()["e"]), bits(noise["fused"]))
+    ten.close()
+    with pytest.raises(Exception):
+        M.PointMassModel(K, T, 0.1, 2 * A, A, philox_rounds=8)

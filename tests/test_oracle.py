@@ -228,6 +228,15 @@ def test_philox_known_answer_vectors(oracle):
     ]
     for ctr, key, want in kats:
         assert oracle.philox(ctr, key) == want
+    # philox4x32 with 7 rounds (mppi_params.philox_rounds = 7), same kat_vectors file
+    kats7 = [
+        ([0, 0, 0, 0], [0, 0], [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a]),
+    ]
+    for ctr, key, want in kats7:
+        assert oracle.philox(ctr, key, rounds=7) == want
 
 
 def test_sampler_statistics_and_shard_independence(oracle):
