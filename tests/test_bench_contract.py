@@ -68,3 +68,28 @@ def test_product_arm_prints_contract_line():
     assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] > 0
     assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["scaling"] == "strong"
+
+
+def test_quoted_dram_traffic_is_not_stale():
+    """bench.py quotes `roofline.traffic` from profiles/*_traffic.json (ncu captures): every file
+    names the commit it was captured at and the kernel sources it depends on, and none of those
+    sources may have changed since (re-capture with tools/jobs/r2b_final1.sh).  Needs the git
+    history: skipped where the tree travels without it (the GPU boxes)."""
+    import json
+    import subprocess
+    from conftest import ROOT
+    if not os.path.isdir(os.path.join(ROOT, ".git")):
+        pytest.skip("no git history here")
+
+    def git(*a):
+        return subprocess.run(["git", "-C", ROOT] + list(a), capture_output=True, text=True)
+
+    for name in ("step_traffic.json", "average_traffic.json", "tile_traffic.json"):
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        assert d.get("commit") and d.get("kernel_sources"), name
+        assert git("cat-file", "-e", d["commit"] + "^{commit}").returncode == 0, (name, d["commit"])
+        for src in d["kernel_sources"]:
+            last = git("log", "-1", "--format=%H", "--", src).stdout.strip()
+            # the capture's commit must contain the last change of the source
+            assert git("merge-base", "--is-ancestor", last, d["commit"]).returncode == 0, \
+                f"{src} changed after the capture quoted in profiles/{name}"

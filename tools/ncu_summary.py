@@ -10,6 +10,11 @@ WANT = [
     'launch__occupancy_limit_registers', 'launch__grid_size', 'launch__block_size',
     'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active',
+    'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed',
+    'sm__pipe_fmaheavy_cycles_active.max.pct_of_peak_sustained_elapsed',
+    'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed',
+    'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed',
+    'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed',
     'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
