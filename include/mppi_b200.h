@@ -66,20 +66,21 @@ extern "C" {
 #define MPPI_FLAG_STEP_KERNEL     (1u << 7)  /* the whole control step as ONE persistent kernel:
                                                sampling + rollout warps and the TMA-fed
                                                weighted-average warps share every SM, so the
-                                               issue-bound and the HBM-bound halves overlap.
+                                               arithmetic-bound and the HBM-bound halves overlap.
                                                Sampled noise, single shard, T*A small enough for
                                                the shared-memory row sums; otherwise the step
                                                silently uses the kernel chain                */
 
-#define MPPI_FLAG_AUTO_CHAIN      (1u << 8)  /* let the library pick the kernel chain from the
-                                               shard's work (measured on B200, every T and A):
-                                               the one-kernel step once its rollout warps run
-                                               >= 1.4 tiles each and a pass over eps is >= 350 MB
-                                               (single shard or MPPI_COMM_P2P); else
-                                               MPPI_FLAG_FUSED_SAMPLING while the fused kernel
-                                               keeps >= 1.55 warps per SM sub-partition (about
-                                               1.2e5 samples on 148 SMs); else the unfused
-                                               chain with MPPI_FLAG_PIPELINED_SAMPLING.
+#define MPPI_FLAG_AUTO_CHAIN      (1u << 8)  /* let the library pick the kernel chain from an
+                                               estimate of what each costs on this shard (a cost
+                                               model fitted on B200 over 112 shapes: the rollouts
+                                               are bound by the FMA pipe of the fullest SM
+                                               sub-partition, the eps passes by HBM): the
+                                               one-kernel step (single shard or MPPI_COMM_P2P),
+                                               MPPI_FLAG_FUSED_SAMPLING, or the unfused chain
+                                               with MPPI_FLAG_PIPELINED_SAMPLING.  At T=200, A=3:
+                                               unfused up to ~1.1e5 samples per GPU, fused up to
+                                               ~3.5e5, the one-kernel step above.
                                                mppi_get_flags returns the choice.             */
 
 #define MPPI_FLAG_PIPELINED_SAMPLING (1u << 9) /* unfused chain only, a LATENCY option for closed
