@@ -225,6 +225,11 @@ __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsign
 {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys_v2_u64(unsigned long long *p, unsigned long long a,
+                                                      unsigned long long b)
+{
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
 {
     unsigned long long v;

@@ -90,11 +90,17 @@ __device__ __forceinline__ bool xchg_merge_body(long long *s_acc, int R,
     const int par = (int)(seq & 1ull);
     const unsigned long long mine = ctl->min_key;
     if (threadIdx.x == 0) ctl->t_xchg[0] = globaltimer_ns();
+    // 16-byte stores (the accumulators start 32 bytes into a 128-byte aligned slot): half as many
+    // NVLink writes to wait for at the fence
+    const int npair = (R + 1) / 2;
     for (int r = 0; r < world; ++r) {
         unsigned long long *slot = mb_slot(xa.peers.mb[r], par, world, rank, sw);
         if (threadIdx.x == 0) st_relaxed_sys_u64(slot + 1, mine);
-        for (int i = threadIdx.x; i <= R; i += nthr)
-            st_relaxed_sys_u64(slot + kMailboxHeaderWords + i, (unsigned long long)s_acc[i]);
+        for (int i = threadIdx.x; i < npair; i += nthr)
+            st_relaxed_sys_v2_u64(slot + kMailboxHeaderWords + 2 * i, (unsigned long long)s_acc[2 * i],
+                                  (unsigned long long)s_acc[2 * i + 1]);
+        if (((R + 1) & 1) && threadIdx.x == 0)
+            st_relaxed_sys_u64(slot + kMailboxHeaderWords + R, (unsigned long long)s_acc[R]);
     }
     __threadfence_system();
     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nthr) : "memory");
@@ -107,8 +113,10 @@ __device__ __forceinline__ bool xchg_merge_body(long long *s_acc, int R,
     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nthr) : "memory");
     if (*reinterpret_cast<volatile unsigned int *>(&ctl->comm_error)) return false;
     unsigned long long *my = xa.peers.mb[rank] + (size_t)par * world * sw;      // local memory
-    if (threadIdx.x == 0) {
-        ctl->t_xchg[2] = globaltimer_ns();
+    if (threadIdx.x == 0) ctl->t_xchg[2] = globaltimer_ns();
+    if (threadIdx.x < world) {
+        // thread r forms the factor of shard r; every one of them reads all keys (independent
+        // loads, in flight together) and takes the same minimum
         unsigned long long keys[kMaxWorld];
         unsigned long long gkey = kMinKeyInit;
 #pragma unroll
@@ -119,14 +127,13 @@ __device__ __forceinline__ bool xchg_merge_body(long long *s_acc, int R,
             }
         const float beta = ordered_to_float((uint32_t)(gkey >> 32));
         const float nil = prob->neg_inv_lambda;
+        unsigned long long kr = kMinKeyInit;
 #pragma unroll
         for (int r = 0; r < kMaxWorld; ++r)
-            if (r < world) {
-                const float beta_r = ordered_to_float((uint32_t)(keys[r] >> 32));
-                s_f[r] = keys[r] == kMinKeyInit ? 0.0
-                                                : (double)expf(__fmul_rn(nil, __fsub_rn(beta_r, beta)));
-            }
-        ctl->min_key = gkey;                      // beta / argmin of the whole step
+            if (r == (int)threadIdx.x) kr = keys[r];
+        const float beta_r = ordered_to_float((uint32_t)(kr >> 32));
+        s_f[threadIdx.x] = kr == kMinKeyInit ? 0.0 : (double)expf(__fmul_rn(nil, __fsub_rn(beta_r, beta)));
+        if (threadIdx.x == 0) ctl->min_key = gkey;         // beta / argmin of the whole step
     }
     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nthr) : "memory");
     for (int i = threadIdx.x; i <= R; i += nthr) {
