@@ -268,6 +268,13 @@ int mppi_shard_range(int64_t samples, int rank, int world_size, int64_t *k_begin
                      int64_t *k_end);
 int mppi_local_samples(mppi_handle *h, int64_t *k_local, int64_t *k_offset);
 
+/* What MPPI_FLAG_AUTO_CHAIN would decide for a shard of samples_local rollouts on a GPU with
+ * num_sms SMs, and why: the estimated microseconds per control step of the unfused chain, the fused
+ * chain and the one-kernel step (est_us[0..2]; constants fitted on B200) and the flag of the chosen
+ * chain (MPPI_FLAG_PIPELINED_SAMPLING = unfused).  Pure host arithmetic (no device needed). */
+int mppi_chain_estimate(int64_t samples_local, int horizon, int act_dim, int num_sms,
+                        double est_us[3], uint32_t *choice);
+
 /* Timing helpers on the handle's stream (CUDA events). */
 int mppi_timer_start(mppi_handle *h);
 int mppi_timer_stop(mppi_handle *h, float *elapsed_ms);

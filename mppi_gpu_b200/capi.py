@@ -45,7 +45,7 @@ EXPORTS = [
     "mppi_set_terminal_weights", "mppi_set_state",
     "mppi_step", "mppi_step_enqueue", "mppi_step_wait", "mppi_get_u", "mppi_set_u",
     "mppi_get_info", "mppi_get_flags", "mppi_get_step_info", "mppi_set_noise", "mppi_set_noise_mode",
-    "mppi_sample_only", "mppi_shard_range", "mppi_local_samples", "mppi_timer_start", "mppi_timer_stop",
+    "mppi_sample_only", "mppi_shard_range", "mppi_local_samples", "mppi_chain_estimate", "mppi_timer_start", "mppi_timer_stop",
     "mppi_set_profiling", "mppi_get_kernel_times", "mppi_get_exchange_times", "mppi_get_launch_count", "mppi_kernel_name",
     "mppi_comm_unique_id", "mppi_comm_p2p_handle", "mppi_comm_p2p_connect", "mppi_last_error",
     "mppi_abi_version",
@@ -116,6 +116,8 @@ def load():
     L.mppi_destroy.argtypes = [H]
     L.mppi_set_problem.argtypes = [H, fp, fp, fp, fp]
     L.mppi_set_terminal_weights.argtypes = [H, fp]
+    L.mppi_chain_estimate.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                      C.POINTER(C.c_uint32)]
     L.mppi_set_state.argtypes = [H, fp]
     L.mppi_step.argtypes = [H, fp]
     L.mppi_step_enqueue.argtypes = [H]
@@ -163,3 +165,12 @@ def shard_range(samples, rank, world_size):
 
 def f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def chain_estimate(samples_local, horizon, act_dim, num_sms=148):
+    """(est_us = {unfused, fused, step}, chosen flag) of MPPI_FLAG_AUTO_CHAIN for a shard; host only."""
+    est = (C.c_double * 3)()
+    ch = C.c_uint32(0)
+    check(load().mppi_chain_estimate(int(samples_local), int(horizon), int(act_dim), int(num_sms), est,
+                                     C.byref(ch)))
+    return {"unfused": est[0], "fused": est[1], "step": est[2]}, int(ch.value)

@@ -818,6 +818,24 @@ int mppi_shard_range(int64_t samples, int rank, int world_size, int64_t *k_begin
     return MPPI_OK;
 }
 
+int mppi_chain_estimate(int64_t samples_local, int horizon, int act_dim, int num_sms,
+                        double est_us[3], uint32_t *choice)
+{
+    if (samples_local < 1 || horizon < 1 || act_dim < 1 || act_dim > MPPI_MAX_ACT || num_sms < 1)
+        return fail(MPPI_ERR_INVALID, "mppi_chain_estimate: bad arguments");
+    LaunchCtx c{};
+    c.k_local = samples_local;
+    c.k_pad = (samples_local + kKPad - 1) / kKPad * kKPad;
+    c.horizon = horizon;
+    c.act_dim = act_dim;
+    c.rows = horizon * act_dim;
+    c.num_sms = num_sms;
+    const ChainCost k = chain_cost(c);
+    if (est_us) { est_us[0] = k.unfused; est_us[1] = k.fused; est_us[2] = k.step; }
+    if (choice) *choice = auto_chain(c, step_kernel_supported(horizon, act_dim, c.k_pad, num_sms));
+    return MPPI_OK;
+}
+
 int mppi_local_samples(mppi_handle *h, int64_t *k_local, int64_t *k_offset)
 {
     if (h && !h->children.empty()) {

@@ -122,3 +122,35 @@ def test_header_is_plain_c_and_links(tmp_path):
                     "-I", os.path.join(ROOT, "include"), "-L", libdir, "-lmppi_b200",
                     f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_auto_chain_policy_against_the_recorded_sweep():
+    """MPPI_FLAG_AUTO_CHAIN decides from a cost model (controller.cu: chain_cost), exposed as
+    mppi_chain_estimate (host arithmetic).  Against the recorded sweep of the three chains on one
+    B200 (profiles/r02_chain_sweep_v2.jsonl: 7 (A, T) shapes x 16 shard sizes): the chosen chain's
+    measured time is within 5 % (+1.5 us) of the fastest on every shape, and the estimate of the
+    chosen chain is within 30 % of its measurement from 1e5 samples up."""
+    import json
+    path = os.path.join(ROOT, "profiles", "r02_chain_sweep_v2.jsonl")
+    rows = [json.loads(l) for l in open(path)]
+    assert len(rows) >= 100
+    fam = {capi.FLAG_PIPELINED_SAMPLING: "unfused", capi.FLAG_FUSED_SAMPLING: "fused",
+           capi.FLAG_STEP_KERNEL: "step"}
+    for r in rows:
+        est, choice = capi.chain_estimate(r["K"], r["T"], r["A"], 148)
+        ms = {k: v for k, v in r["ms"].items() if k in ("unfused", "fused", "step")}
+        best = min(ms.values())
+        got = ms[fam[choice]]
+        assert got <= 1.05 * best + 1.5e-3, (r["A"], r["T"], r["K"], fam[choice], ms)
+        if r["K"] >= 100000:
+            k = fam[choice]
+            assert abs(est[k] / (got * 1e3) - 1.0) < 0.30, (r["A"], r["T"], r["K"], k, est[k], got)
+    # clear cases (the GPU test test_auto_chain_picks_by_work asks the handle for the same)
+    assert capi.chain_estimate(30000, 200, 2)[1] == capi.FLAG_PIPELINED_SAMPLING
+    assert capi.chain_estimate(150000, 200, 2)[1] == capi.FLAG_FUSED_SAMPLING
+    assert capi.chain_estimate(450000, 10, 2)[1] == capi.FLAG_FUSED_SAMPLING
+    assert capi.chain_estimate(700000, 120, 2)[1] == capi.FLAG_STEP_KERNEL
+    # the rollout cost is a step function of the warps on the fullest sub-partition
+    e1, _ = capi.chain_estimate(150000, 200, 3)
+    e2, _ = capi.chain_estimate(166667, 200, 3)
+    assert e2["fused"] - e1["fused"] > 40.0
